@@ -1,0 +1,74 @@
+"""Builds liblcgs_b200.so (the C-ABI library) in-tree with nvcc for sm_100a.
+
+No torch, no JIT cache: the .so lands next to the sources so that it travels to the GPU box with
+the repository snapshot.  Flags that matter:
+  -gencode arch=compute_100a,code=sm_100a   B200 only
+  --fmad=false                              the arithmetic contract (see csrc/lcgs_math.cuh)
+  -lineinfo                                 so ncu's source page maps to our code
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(CSRC, "build")
+LIB = os.path.join(HERE, "liblcgs_b200.so")
+SOURCES = ["capi.cu", "preprocess.cu", "scan.cu", "binning.cu", "sort.cu", "blend.cu"]
+HEADERS = ["common.cuh", "lcgs_math.cuh", os.path.join("..", "..", "include", "lcgs_b200.h")]
+
+NVCC = os.environ.get("LCGS_NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off", "-Xptxas", "-v", "-ccbin", "g++",
+]
+
+
+def _mtime(path: str) -> float:
+    return os.path.getmtime(path) if os.path.exists(path) else 0.0
+
+
+def is_stale() -> bool:
+    newest = max([_mtime(os.path.join(CSRC, f)) for f in SOURCES + HEADERS] + [_mtime(__file__)])
+    return _mtime(LIB) < newest
+
+
+def build_native(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB
+    if not os.path.exists(NVCC):
+        raise RuntimeError("nvcc not found at %s and %s is missing or stale" % (NVCC, LIB))
+    os.makedirs(BUILD, exist_ok=True)
+    log_path = os.path.join(BUILD, "ptxas.log")
+
+    def compile_one(src: str):
+        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        cmd = [NVCC, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, r
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    with open(log_path, "w") as log:
+        for src, _, r in results:
+            log.write("==== %s ====\n%s\n%s\n" % (src, r.stdout, r.stderr))
+    for src, _, r in results:
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed on %s" % src)
+        if verbose:
+            sys.stderr.write(r.stderr)
+    objs = [o for _, o, _ in results]
+    link = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++"]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_native(force="--force" in sys.argv, verbose=True))

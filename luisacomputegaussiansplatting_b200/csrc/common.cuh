@@ -1,0 +1,120 @@
+// common.cuh -- context, workspace and launch helpers shared by the stage kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/lcgs_b200.h"
+#include "lcgs_math.cuh"
+
+namespace lcgs_b200 {
+
+constexpr int kNumSMs = 148;  // B200; the real count is queried at ctx creation
+
+// Per-Gaussian record the blend kernel gathers: three float4 (48 B, two 32-B sectors).
+//   r0 = (pix.x, pix.y, -0.5*conic.x, -conic.y)
+//   r1 = (-0.5*conic.z, power threshold of the alpha test, opacity, cull radius^2)
+//   r2 = (red, green, blue, 0)
+constexpr int kRecordFloat4s = 3;
+
+// Radix sort geometry (onesweep): 8-bit digits.
+constexpr int kRadixBits      = 8;
+constexpr int kRadix          = 1 << kRadixBits;
+constexpr int kSortThreads    = 256;
+constexpr int kSortItems      = 16;
+constexpr int kSortTile       = kSortThreads * kSortItems;  // 4096 pairs per tile
+constexpr int kMaxSortPasses  = 8;
+
+// Scan geometry (decoupled look-back).
+constexpr int kScanThreads = 256;
+constexpr int kScanItems   = 16;
+constexpr int kScanTile    = kScanThreads * kScanItems;
+
+struct Workspace {
+    void*  ptr   = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace lcgs_b200
+
+// The opaque context of the C ABI.
+struct lcgs_b200_ctx {
+    int          device     = 0;
+    int          num_sms    = lcgs_b200::kNumSMs;
+    char         last_error[256];
+    // device scalars: [0] num_rendered (instances), [1] overflow flag, [2..] tickets
+    uint32_t*    d_scalars  = nullptr;
+    uint32_t*    h_scalars  = nullptr;  // pinned mirror
+    // workspaces, grown geometrically and never shrunk (like ensure_*_temp_buffer,
+    // lcgs/src/gs_tile_splatter/impl.cpp:31-61)
+    lcgs_b200::Workspace scan_ws;     // look-back tile status
+    lcgs_b200::Workspace sort_ws;     // histograms + look-back status + ping-pong pair buffer
+    lcgs_b200::Workspace record_ws;   // packed per-Gaussian blend records
+    // per-stage timing
+    int          profiling  = 0;
+    cudaEvent_t  ev[16];
+    int          ev_count   = 0;
+    int          ev_valid   = 0;
+    cudaEvent_t  done_event = nullptr;
+};
+
+#define LCGS_SCALAR_NUM_RENDERED 0
+#define LCGS_SCALAR_OVERFLOW     1
+#define LCGS_SCALAR_SCAN_TICKET  2
+#define LCGS_SCALAR_SORT_TICKET  3   /* .. 3 + kMaxSortPasses - 1 */
+#define LCGS_SCALAR_DUP_TICKET   12
+#define LCGS_NUM_SCALARS         16
+
+#define LCGS_CUDA_CHECK(ctx, expr)                                                                   \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            if (ctx)                                                                                 \
+                snprintf((ctx)->last_error, sizeof((ctx)->last_error), "%s:%d: %s: %s", __FILE__,    \
+                         __LINE__, #expr, cudaGetErrorString(e__));                                  \
+            return LCGS_B200_ERR_CUDA;                                                               \
+        }                                                                                            \
+    } while (0)
+
+#define LCGS_REQUIRE(ctx, cond, msg)                                                                 \
+    do {                                                                                             \
+        if (!(cond)) {                                                                               \
+            if (ctx) snprintf((ctx)->last_error, sizeof((ctx)->last_error), "%s", msg);              \
+            return LCGS_B200_ERR_INVALID;                                                            \
+        }                                                                                            \
+    } while (0)
+
+namespace lcgs_b200 {
+
+int ws_reserve(lcgs_b200_ctx* ctx, Workspace& ws, size_t bytes);
+
+// stage launchers (one group per .cu); all enqueue on `s` and return an lcgs_b200_status
+int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b200_view_params* vp,
+                            const lcgs_b200_frame* fr, float4* records, cudaStream_t s);
+int launch_sh(lcgs_b200_ctx* ctx, int P, int deg, const float* cam_pos, const float* pos, const float* sh, float* color,
+              cudaStream_t s);
+int launch_project(lcgs_b200_ctx* ctx, int P, const float* pos, const float* scale, const float* rotq,
+                   float scale_modifier, const ViewParams& vp, float* means_2d, float* depth, float* covs_2d,
+                   cudaStream_t s);
+int launch_allocate_tiles(lcgs_b200_ctx* ctx, int P, int W, int H, const float* depth, float* means_2d, float* covs_2d,
+                          uint32_t* tiles_touched, int32_t* radii, int row0, int row1, cudaStream_t s);
+int launch_build_records(lcgs_b200_ctx* ctx, int P, const float* means_2d, const float* conic, const float* opacity,
+                         const float* color, const uint32_t* tiles_touched, float4* records, cudaStream_t s);
+int launch_scan(lcgs_b200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t n, uint32_t* d_total, cudaStream_t s);
+int launch_duplicate_keys(lcgs_b200_ctx* ctx, int P, int W, int H, const float* means_2d, const uint32_t* offsets,
+                          const int32_t* radii, const float* depth, uint64_t* keys, uint32_t* vals, size_t capacity,
+                          int row0, int row1, cudaStream_t s);
+size_t sort_temp_bytes(size_t n);
+int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
+                uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
+                cudaStream_t s);
+int launch_ranges(lcgs_b200_ctx* ctx, const uint64_t* keys, size_t n_host, const uint32_t* d_n, size_t capacity,
+                  uint32_t* ranges, int num_tiles, cudaStream_t s);
+int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32_t* ranges, const uint32_t* point_list,
+                 const float4* records, const uint32_t* d_num_rendered, float* img, int row0, int row1, cudaStream_t s);
+int launch_fill_u32(lcgs_b200_ctx* ctx, uint32_t* buf, size_t n, uint32_t v, cudaStream_t s);
+int launch_fill_u64(lcgs_b200_ctx* ctx, uint64_t* buf, size_t n, uint64_t v, cudaStream_t s);
+int launch_fill_f32(lcgs_b200_ctx* ctx, float* buf, size_t n, float v, cudaStream_t s);
+
+}  // namespace lcgs_b200

@@ -1,0 +1,305 @@
+// preprocess.cu -- stage 1: per-Gaussian work.
+//
+//  * preprocess_fused_kernel : SH colour (K1) + projection/EWA (K2) + conic/radius/tile rect (K3)
+//    in one pass over the Gaussians, plus the packed 48-byte record the blend kernel gathers.
+//    Replaces three DSL kernels with HBM round trips in between (sh_preprocessor.cpp:159-166,
+//    gs_projector/shader.cpp:82-139, gs_tile_splatter/shader.cpp:102-163).
+//  * sh_kernel / project_kernel / allocate_tiles_kernel / build_records_kernel : the same
+//    arithmetic behind the reference's separate entry points.
+//
+// HBM-bound: algorithmic bytes per Gaussian = 40 (pos, scale, rotq) + 192 (SH, only when the
+// Gaussian touches a tile) + outputs.  SH rows are fetched with block-cooperative, fully coalesced
+// float4 loads predicated on "touches a tile", staged in padded shared memory (row stride 13
+// float4 -> conflict-free LDS.128), so invisible/off-screen Gaussians never read their 192 bytes.
+#include "common.cuh"
+
+namespace lcgs_b200 {
+
+struct PreprocessArgs {
+    int          P, sh_deg;
+    const float* pos;
+    const float* scale;
+    const float* rotq;
+    const float* sh;
+    const float* opacity;
+    float        scale_modifier;
+    ViewParams   vp;
+    uint32_t     gx, gy, row0, row1;
+    float*       means_2d;  // optional
+    float*       depth;
+    float*       conic;  // optional
+    float*       color;  // optional
+    int32_t*     radii;
+    uint32_t*    tiles;
+    float4*      records;
+};
+
+constexpr int kPreThreads = 128;
+constexpr int kShRowF4    = 12;  // 16 coefficients x RGB = 48 floats = 12 float4
+constexpr int kShRowPad   = 13;  // padded row stride in float4
+
+struct RegSh {
+    const float* r;
+    __device__ __forceinline__ float operator()(int k, int c) const { return r[k * 3 + c]; }
+};
+
+struct GlobalSh {
+    const float* p;
+    __device__ __forceinline__ float operator()(int k, int c) const { return __ldg(p + k * 3 + c); }
+};
+
+__device__ __forceinline__ void write_record(float4* rec, const Splat2D& s, float op, const float* rgb)
+{
+    const float thr = alpha_threshold(op);
+    rec[0] = make_float4(s.px, s.py, -0.5f * s.conic[0], -s.conic[1]);
+    rec[1] = make_float4(-0.5f * s.conic[2], thr, op, INFINITY);
+    rec[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+}
+
+__global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __grid_constant__ PreprocessArgs a)
+{
+    __shared__ float4  s_sh[kPreThreads * kShRowPad];
+    __shared__ uint8_t s_need[kPreThreads];
+
+    const int  t  = threadIdx.x;
+    const long g0 = (long)blockIdx.x * kPreThreads;
+    const long i  = g0 + t;
+
+    // ---- phase 1: geometry ----------------------------------------------------------------
+    float   px = 0.f, py = 0.f, pz = 0.f;
+    Splat2D s;
+    s.tiles   = 0;
+    bool need = false;
+    if (i < a.P) {
+        px = __ldg(a.pos + 3 * i);
+        py = __ldg(a.pos + 3 * i + 1);
+        pz = __ldg(a.pos + 3 * i + 2);
+        const ViewPoint pv = view_transform(a.vp, px, py, pz);
+        if (pv.visible) {
+            const float  s0 = __ldg(a.scale + 3 * i), s1 = __ldg(a.scale + 3 * i + 1), s2 = __ldg(a.scale + 3 * i + 2);
+            const float4 q  = __ldg(reinterpret_cast<const float4*>(a.rotq) + i);
+            float        cov[3];
+            ewa_cov2d(a.vp, pv, a.scale_modifier, s0, s1, s2, q.x, q.y, q.z, q.w, cov);
+            s = splat_from_cov(pv.ndc_x, pv.ndc_y, cov, a.vp.width, a.vp.height, a.gx, a.gy, a.row0, a.row1);
+            a.depth[i] = pv.z;
+            a.radii[i] = s.radius;
+            a.tiles[i] = s.tiles;
+            if (a.means_2d) reinterpret_cast<float2*>(a.means_2d)[i] = make_float2(s.px, s.py);
+            if (a.conic) {
+                a.conic[3 * i]     = s.conic[0];
+                a.conic[3 * i + 1] = s.conic[1];
+                a.conic[3 * i + 2] = s.conic[2];
+            }
+            need = s.tiles > 0u;
+        } else {
+            // defined behaviour for near-culled Gaussians (the reference leaves stale data, Q6)
+            a.depth[i] = 0.0f;
+            a.radii[i] = 0;
+            a.tiles[i] = 0u;
+            if (a.means_2d) reinterpret_cast<float2*>(a.means_2d)[i] = make_float2(0.f, 0.f);
+            if (a.conic) {
+                a.conic[3 * i]     = 0.f;
+                a.conic[3 * i + 1] = 0.f;
+                a.conic[3 * i + 2] = 0.f;
+            }
+        }
+    }
+    s_need[t] = need ? 1 : 0;
+    __syncthreads();
+
+    // ---- phase 2: coalesced, predicated SH fetch into padded shared memory -------------------
+    if (a.sh_deg == 3) {
+        const float4* src = reinterpret_cast<const float4*>(a.sh) + g0 * kShRowF4;
+        float4        v[kShRowF4];
+        int           dst[kShRowF4];
+#pragma unroll
+        for (int j = 0; j < kShRowF4; j++) {
+            const int idx = j * kPreThreads + t;
+            const int g   = idx / kShRowF4;
+            const int c   = idx - g * kShRowF4;
+            const bool on = s_need[g] != 0;  // implies g0 + g < P
+            dst[j]        = on ? g * kShRowPad + c : -1;
+            if (on) v[j] = __ldg(src + idx);
+        }
+#pragma unroll
+        for (int j = 0; j < kShRowF4; j++)
+            if (dst[j] >= 0) s_sh[dst[j]] = v[j];
+    }
+    __syncthreads();
+
+    // ---- phase 3: colour + blend record ------------------------------------------------------
+    if (need) {
+        float rgb[3];
+        if (a.sh_deg == 3) {
+            float r[48];
+#pragma unroll
+            for (int k = 0; k < kShRowF4; k++) {
+                const float4 q = s_sh[t * kShRowPad + k];
+                r[4 * k] = q.x; r[4 * k + 1] = q.y; r[4 * k + 2] = q.z; r[4 * k + 3] = q.w;
+            }
+            sh_color(3, a.vp.cam_pos, px, py, pz, RegSh{ r }, rgb);
+        } else {
+            const int feat = (a.sh_deg + 1) * (a.sh_deg + 1);
+            sh_color(a.sh_deg, a.vp.cam_pos, px, py, pz, GlobalSh{ a.sh + (size_t)i * feat * 3 }, rgb);
+        }
+        if (a.color) {
+            a.color[3 * i]     = rgb[0];
+            a.color[3 * i + 1] = rgb[1];
+            a.color[3 * i + 2] = rgb[2];
+        }
+        write_record(a.records + (size_t)i * kRecordFloat4s, s, __ldg(a.opacity + i), rgb);
+    }
+}
+
+// ---- the reference's separate passes -----------------------------------------------------------
+
+__global__ void __launch_bounds__(256) sh_kernel(int P, int deg, float cx, float cy, float cz, const float* __restrict__ pos,
+                                                 const float* __restrict__ sh, float* __restrict__ color)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float cam[3] = { cx, cy, cz };
+    const int   feat   = (deg + 1) * (deg + 1);
+    float       rgb[3];
+    sh_color(deg, cam, __ldg(pos + 3 * i), __ldg(pos + 3 * i + 1), __ldg(pos + 3 * i + 2),
+             GlobalSh{ sh + (size_t)i * feat * 3 }, rgb);
+    color[3 * i]     = rgb[0];
+    color[3 * i + 1] = rgb[1];
+    color[3 * i + 2] = rgb[2];
+}
+
+__global__ void __launch_bounds__(256)
+    project_kernel(int P, const float* __restrict__ pos, const float* __restrict__ scale, const float* __restrict__ rotq,
+                   float scale_modifier, const __grid_constant__ ViewParams vp, float* __restrict__ means_2d,
+                   float* __restrict__ depth, float* __restrict__ covs_2d)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const ViewPoint pv = view_transform(vp, __ldg(pos + 3 * i), __ldg(pos + 3 * i + 1), __ldg(pos + 3 * i + 2));
+    float           cov[3] = { 0.f, 0.f, 0.f };
+    float           d = 0.f, nx = 0.f, ny = 0.f;
+    if (pv.visible) {
+        ewa_cov2d(vp, pv, scale_modifier, __ldg(scale + 3 * i), __ldg(scale + 3 * i + 1), __ldg(scale + 3 * i + 2),
+                  __ldg(rotq + 4 * i), __ldg(rotq + 4 * i + 1), __ldg(rotq + 4 * i + 2), __ldg(rotq + 4 * i + 3), cov);
+        d  = pv.z;
+        nx = pv.ndc_x;
+        ny = pv.ndc_y;
+    }
+    depth[i]            = d;
+    means_2d[2 * i]     = nx;
+    means_2d[2 * i + 1] = ny;
+    covs_2d[3 * i]      = cov[0];
+    covs_2d[3 * i + 1]  = cov[1];
+    covs_2d[3 * i + 2]  = cov[2];
+}
+
+__global__ void __launch_bounds__(256)
+    allocate_tiles_kernel(int P, int W, int H, uint32_t gx, uint32_t gy, uint32_t row0, uint32_t row1,
+                          const float* __restrict__ depth, float* __restrict__ means_2d, float* __restrict__ covs_2d,
+                          uint32_t* __restrict__ tiles_touched, int32_t* __restrict__ radii)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    int32_t  radius = 0;
+    uint32_t tiles  = 0;
+    if (!(depth[i] < 0.2f)) {
+        const float   cov[3] = { covs_2d[3 * i], covs_2d[3 * i + 1], covs_2d[3 * i + 2] };
+        const Splat2D s      = splat_from_cov(means_2d[2 * i], means_2d[2 * i + 1], cov, W, H, gx, gy, row0, row1);
+        radius               = s.radius;
+        tiles                = s.tiles;
+        covs_2d[3 * i]       = s.conic[0];
+        covs_2d[3 * i + 1]   = s.conic[1];
+        covs_2d[3 * i + 2]   = s.conic[2];
+        means_2d[2 * i]      = s.px;
+        means_2d[2 * i + 1]  = s.py;
+    }
+    radii[i]         = radius;
+    tiles_touched[i] = tiles;
+}
+
+// Packs the reference-layout buffers (after allocate_tiles) into blend records.
+__global__ void __launch_bounds__(256)
+    build_records_kernel(int P, const float* __restrict__ means_2d, const float* __restrict__ conic,
+                         const float* __restrict__ opacity, const float* __restrict__ color,
+                         const uint32_t* __restrict__ tiles_touched, float4* __restrict__ records)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (tiles_touched && tiles_touched[i] == 0u) return;
+    Splat2D s;
+    s.px       = means_2d[2 * i];
+    s.py       = means_2d[2 * i + 1];
+    s.conic[0] = conic[3 * i];
+    s.conic[1] = conic[3 * i + 1];
+    s.conic[2] = conic[3 * i + 2];
+    const float rgb[3] = { color[3 * i], color[3 * i + 1], color[3 * i + 2] };
+    write_record(records + (size_t)i * kRecordFloat4s, s, opacity[i], rgb);
+}
+
+// ---- launchers -------------------------------------------------------------------------------
+
+static inline uint32_t div_up(long a, long b) { return (uint32_t)((a + b - 1) / b); }
+
+int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b200_view_params* vp,
+                            const lcgs_b200_frame* fr, float4* records, cudaStream_t s)
+{
+    const int P = sc->num_gaussians;
+    if (P <= 0) return LCGS_B200_OK;
+    PreprocessArgs a;
+    a.P = P; a.sh_deg = sc->sh_deg;
+    a.pos = sc->pos; a.scale = sc->scale; a.rotq = sc->rotq; a.sh = sc->sh; a.opacity = sc->opacity;
+    a.scale_modifier = sc->scale_modifier;
+    static_assert(sizeof(ViewParams) == sizeof(lcgs_b200_view_params), "view params layout");
+    memcpy(&a.vp, vp, sizeof(ViewParams));
+    a.gx   = (uint32_t)((fr->width + 15) / 16);
+    a.gy   = (uint32_t)((fr->height + 15) / 16);
+    a.row0 = (uint32_t)fr->tile_row_begin;
+    a.row1 = fr->tile_row_end < 0 ? a.gy : (uint32_t)fr->tile_row_end;
+    a.means_2d = fr->means_2d; a.depth = fr->depth; a.conic = fr->conic; a.color = fr->color;
+    a.radii = fr->radii; a.tiles = fr->tiles_touched; a.records = records;
+    preprocess_fused_kernel<<<div_up(P, kPreThreads), kPreThreads, 0, s>>>(a);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+int launch_sh(lcgs_b200_ctx* ctx, int P, int deg, const float* cam_pos, const float* pos, const float* sh, float* color,
+              cudaStream_t s)
+{
+    if (P <= 0) return LCGS_B200_OK;
+    sh_kernel<<<div_up(P, 256), 256, 0, s>>>(P, deg, cam_pos[0], cam_pos[1], cam_pos[2], pos, sh, color);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+int launch_project(lcgs_b200_ctx* ctx, int P, const float* pos, const float* scale, const float* rotq,
+                   float scale_modifier, const ViewParams& vp, float* means_2d, float* depth, float* covs_2d,
+                   cudaStream_t s)
+{
+    if (P <= 0) return LCGS_B200_OK;
+    project_kernel<<<div_up(P, 256), 256, 0, s>>>(P, pos, scale, rotq, scale_modifier, vp, means_2d, depth, covs_2d);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+int launch_allocate_tiles(lcgs_b200_ctx* ctx, int P, int W, int H, const float* depth, float* means_2d, float* covs_2d,
+                          uint32_t* tiles_touched, int32_t* radii, int row0, int row1, cudaStream_t s)
+{
+    if (P <= 0) return LCGS_B200_OK;
+    const uint32_t gx = (uint32_t)((W + 15) / 16), gy = (uint32_t)((H + 15) / 16);
+    allocate_tiles_kernel<<<div_up(P, 256), 256, 0, s>>>(P, W, H, gx, gy, (uint32_t)row0,
+                                                         row1 < 0 ? gy : (uint32_t)row1, depth, means_2d, covs_2d,
+                                                         tiles_touched, radii);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+int launch_build_records(lcgs_b200_ctx* ctx, int P, const float* means_2d, const float* conic, const float* opacity,
+                         const float* color, const uint32_t* tiles_touched, float4* records, cudaStream_t s)
+{
+    if (P <= 0) return LCGS_B200_OK;
+    build_records_kernel<<<div_up(P, 256), 256, 0, s>>>(P, means_2d, conic, opacity, color, tiles_touched, records);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+}  // namespace lcgs_b200

@@ -1,0 +1,333 @@
+// sort.cu -- stage 4: onesweep least-significant-digit radix sort of (uint64 key, uint32 value)
+// pairs.  Replaces lcpp DeviceRadixSort<>::SortPairs<ulong,uint> (call site
+// lcgs/src/gs_tile_splatter/impl.cpp:134-144), which the reference's README calls crude.
+//
+// One histogram kernel reads the keys once and counts every digit of every pass; then one
+// "onesweep" kernel per 8-bit digit reads each pair once and writes it once to its final place for
+// that pass: tiles (4096 pairs) are ranked in shared memory with warp-match (__match_any_sync)
+// histograms, the per-digit global offsets come from a chained-scan decoupled look-back across
+// tiles, and pairs are staged through shared memory so that global stores are coalesced runs.
+// Stable: ties keep their input order, so equal (tile, depth) keys stay ordered by Gaussian index,
+// exactly what the CPU oracle's stable sort yields.
+//
+// HBM-bound: algorithmic bytes = 8*n (histogram) + 24*n per pass.
+#include "common.cuh"
+
+namespace lcgs_b200 {
+
+constexpr uint32_t kStatusAggregate = 1u << 30;
+constexpr uint32_t kStatusInclusive = 2u << 30;
+constexpr uint32_t kStatusValueMask = (1u << 30) - 1u;
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ size_t resolve_n(size_t n_host, const uint32_t* d_n, size_t capacity)
+{
+    if (!d_n) return n_host;
+    size_t n = *d_n;
+    return n > capacity ? capacity : n;
+}
+
+struct SortPassInfo {
+    int      num_passes;
+    int      shift[kMaxSortPasses];
+    uint32_t mask[kMaxSortPasses];
+};
+
+// ---- upfront histogram of every pass's digit ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+    radix_histogram_kernel(const unsigned long long* __restrict__ keys, size_t n_host, const uint32_t* __restrict__ d_n,
+                           size_t capacity, uint32_t* __restrict__ hist, const __grid_constant__ SortPassInfo info)
+{
+    __shared__ uint32_t s_hist[kMaxSortPasses * kRadix];
+    for (int k = threadIdx.x; k < info.num_passes * kRadix; k += blockDim.x) s_hist[k] = 0u;
+    __syncthreads();
+    const size_t n      = resolve_n(n_host, d_n, capacity);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const unsigned long long key = __ldg(keys + k);
+#pragma unroll
+        for (int p = 0; p < kMaxSortPasses; p++)
+            if (p < info.num_passes) atomicAdd(&s_hist[p * kRadix + (uint32_t)((key >> info.shift[p]) & info.mask[p])], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < info.num_passes * kRadix; k += blockDim.x) {
+        const uint32_t c = s_hist[k];
+        if (c) atomicAdd(hist + k, c);
+    }
+}
+
+// exclusive scan of one value per thread over a 256-thread block
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_warp /* [8] */, uint32_t* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t  x    = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const uint32_t s = s_warp[w];
+        if (w < warp) pre += s;
+        tot += s;
+    }
+    __syncthreads();  // s_warp may be reused
+    if (total) *total = tot;
+    return pre + x - v;
+}
+
+// ---- one onesweep pass -------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads, 2)
+    onesweep_pass_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
+                         const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
+                         const uint32_t* __restrict__ d_n, size_t capacity, const uint32_t* __restrict__ hist /* [256] */,
+                         uint32_t* status /* [tiles][256] */, uint32_t* ticket, int shift, uint32_t mask)
+{
+    __shared__ uint32_t           s_warp_hist[(kSortThreads / 32) * kRadix];  // per-warp digit counters
+    __shared__ unsigned long long s_keys[kSortTile];                          // aliased by the values later
+    __shared__ uint32_t           s_tile_start[kRadix];   // exclusive digit prefix inside the tile
+    __shared__ uint32_t           s_digit_base[kRadix];   // global base of the digit minus s_tile_start
+    __shared__ uint32_t           s_scan[8];
+    __shared__ uint32_t           s_tile;
+    uint32_t* const s_vals = reinterpret_cast<uint32_t*>(s_keys);
+
+    const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL    = 0xFFFFFFFFu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const size_t   n       = resolve_n(n_host, d_n, capacity);
+    const uint32_t num_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+
+    // global exclusive scan of this pass's digit histogram (same for every tile)
+    const uint32_t bin_base = block_exclusive_scan_256(__ldg(hist + tid), s_scan, nullptr);
+
+    for (;;) {
+        __syncthreads();  // previous iteration finished with shared memory
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        for (int k = tid; k < (kSortThreads / 32) * kRadix; k += kSortThreads) s_warp_hist[k] = 0u;
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) break;
+        const size_t   tile_base = (size_t)tile * kSortTile;
+        const uint32_t nvalid    = (uint32_t)((n - tile_base) < (size_t)kSortTile ? (n - tile_base) : (size_t)kSortTile);
+
+        // ---- load (warp-striped: item j of lane l sits at warp*512 + j*32 + l) ----------------
+        unsigned long long key[kSortItems];
+        uint32_t           val[kSortItems];
+#pragma unroll
+        for (int j = 0; j < kSortItems; j++) {
+            const uint32_t q = warp * (kSortItems * 32) + j * 32 + lane;
+            if (q < nvalid) {
+                key[j] = __ldg(keys_in + tile_base + q);
+                val[j] = __ldg(vals_in + tile_base + q);
+            } else {
+                key[j] = ~0ull;
+                val[j] = 0u;
+            }
+        }
+
+        // ---- rank inside the warp with match_any ---------------------------------------------
+        uint32_t  rank[kSortItems];
+        uint32_t* my_hist = s_warp_hist + warp * kRadix;
+#pragma unroll
+        for (int j = 0; j < kSortItems; j++) {
+            const uint32_t q     = warp * (kSortItems * 32) + j * 32 + lane;
+            const bool     valid = q < nvalid;
+            const uint32_t d     = valid ? (uint32_t)((key[j] >> shift) & mask) : (uint32_t)kRadix;
+            const unsigned peers = __match_any_sync(FULL, d);
+            const unsigned lower = peers & lt_mask;
+            uint32_t       pre   = 0;
+            if (valid) pre = my_hist[d];
+            __syncwarp();
+            if (valid && lower == 0u) my_hist[d] = pre + __popc(peers);
+            __syncwarp();
+            rank[j] = pre + __popc(lower);
+        }
+        __syncthreads();
+
+        // ---- per digit (thread d): prefix over warps, tile histogram, look-back ----------------
+        uint32_t tile_count = 0;
+#pragma unroll
+        for (int w = 0; w < kSortThreads / 32; w++) {
+            const uint32_t c           = s_warp_hist[w * kRadix + tid];
+            s_warp_hist[w * kRadix + tid] = tile_count;
+            tile_count += c;
+        }
+        const uint32_t tile_start = block_exclusive_scan_256(tile_count, s_scan, nullptr);
+        s_tile_start[tid]         = tile_start;
+        {
+            uint32_t* my_status = status + (size_t)tile * kRadix + tid;
+            uint32_t  prefix    = 0;
+            if (tile > 0) {
+                st_relaxed_u32(my_status, kStatusAggregate | tile_count);
+                const uint32_t* p = my_status - kRadix;
+                for (;;) {
+                    uint32_t st;
+                    do { st = ld_relaxed_u32(p); } while ((st >> 30) == 0u);
+                    prefix += st & kStatusValueMask;
+                    if ((st >> 30) == 2u) break;
+                    p -= kRadix;
+                }
+            }
+            st_relaxed_u32(my_status, kStatusInclusive | ((prefix + tile_count) & kStatusValueMask));
+            s_digit_base[tid] = bin_base + prefix - tile_start;
+        }
+        __syncthreads();
+
+        // ---- scatter keys into shared memory in tile-sorted order -----------------------------
+#pragma unroll
+        for (int j = 0; j < kSortItems; j++) {
+            const uint32_t q = warp * (kSortItems * 32) + j * 32 + lane;
+            if (q < nvalid) {
+                const uint32_t d = (uint32_t)((key[j] >> shift) & mask);
+                rank[j] += s_tile_start[d] + my_hist[d];
+                s_keys[rank[j]] = key[j];
+            }
+        }
+        __syncthreads();
+
+        // ---- coalesced key write-out; remember each slot's global destination -----------------
+        uint32_t dst[kSortItems];
+#pragma unroll
+        for (int j = 0; j < kSortItems; j++) {
+            const uint32_t q = tid + j * kSortThreads;
+            if (q < nvalid) {
+                const unsigned long long k = s_keys[q];
+                const uint32_t           d = (uint32_t)((k >> shift) & mask);
+                dst[j]                     = s_digit_base[d] + q;
+                keys_out[dst[j]]           = k;
+            }
+        }
+        __syncthreads();
+
+        // ---- same for the values, through the same shared memory ------------------------------
+#pragma unroll
+        for (int j = 0; j < kSortItems; j++) {
+            const uint32_t q = warp * (kSortItems * 32) + j * 32 + lane;
+            if (q < nvalid) s_vals[rank[j]] = val[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kSortItems; j++) {
+            const uint32_t q = tid + j * kSortThreads;
+            if (q < nvalid) vals_out[dst[j]] = s_vals[q];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    copy_pairs_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
+                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
+                      const uint32_t* __restrict__ d_n, size_t capacity)
+{
+    const size_t n      = resolve_n(n_host, d_n, capacity);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        keys_out[k] = keys_in[k];
+        vals_out[k] = vals_in[k];
+    }
+}
+
+// workspace layout: [hist: passes*256 u32][tickets are ctx scalars][status: passes*tiles*256 u32][tmp keys][tmp vals]
+static size_t sort_ws_layout(size_t n, size_t* off_status, size_t* off_keys, size_t* off_vals)
+{
+    const size_t tiles = (n + kSortTile - 1) / kSortTile;
+    size_t       off   = 0;
+    off += (size_t)kMaxSortPasses * kRadix * sizeof(uint32_t);
+    off = (off + 255) & ~(size_t)255;
+    if (off_status) *off_status = off;
+    off += (size_t)kMaxSortPasses * tiles * kRadix * sizeof(uint32_t);
+    off = (off + 255) & ~(size_t)255;
+    if (off_keys) *off_keys = off;
+    off += n * sizeof(uint64_t);
+    off = (off + 255) & ~(size_t)255;
+    if (off_vals) *off_vals = off;
+    off += n * sizeof(uint32_t);
+    off = (off + 255) & ~(size_t)255;
+    return off;
+}
+
+size_t sort_temp_bytes(size_t n) { return sort_ws_layout(n, nullptr, nullptr, nullptr); }
+
+int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
+                uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
+                cudaStream_t s)
+{
+    LCGS_REQUIRE(ctx, begin_bit >= 0 && end_bit <= 64 && begin_bit <= end_bit, "sort: bad bit range");
+    const size_t bound = d_n ? capacity : n_host;  // upper bound on the number of pairs
+    if (bound == 0) return LCGS_B200_OK;
+    LCGS_REQUIRE(ctx, bound <= (size_t)kStatusValueMask, "sort: more than 2^30-1 pairs");
+    if (!d_n) capacity = n_host;
+
+    SortPassInfo info;
+    const int    bits = end_bit - begin_bit;
+    info.num_passes   = (bits + kRadixBits - 1) / kRadixBits;
+    for (int p = 0; p < kMaxSortPasses; p++) {
+        const int lo   = begin_bit + p * kRadixBits;
+        const int w    = (p < info.num_passes) ? ((end_bit - lo) < kRadixBits ? (end_bit - lo) : kRadixBits) : 0;
+        info.shift[p]  = lo < 64 ? lo : 0;
+        info.mask[p]   = w > 0 ? ((1u << w) - 1u) : 0u;
+    }
+
+    const auto* kin  = reinterpret_cast<const unsigned long long*>(keys_in);
+    auto*       kout = reinterpret_cast<unsigned long long*>(keys_out);
+    const unsigned grid_stride_blocks = (unsigned)(((bound + 1023) / 1024) < (size_t)ctx->num_sms * 8
+                                                       ? ((bound + 1023) / 1024)
+                                                       : (size_t)ctx->num_sms * 8);
+    if (info.num_passes == 0) {
+        copy_pairs_kernel<<<grid_stride_blocks, 256, 0, s>>>(kin, kout, vals_in, vals_out, n_host, d_n, capacity);
+        LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+        return LCGS_B200_OK;
+    }
+
+    size_t       off_status, off_keys, off_vals;
+    const size_t bytes = sort_ws_layout(bound, &off_status, &off_keys, &off_vals);
+    int          rc    = ws_reserve(ctx, ctx->sort_ws, bytes);
+    if (rc) return rc;
+    char*     ws        = (char*)ctx->sort_ws.ptr;
+    uint32_t* hist      = (uint32_t*)ws;
+    uint32_t* status    = (uint32_t*)(ws + off_status);
+    auto*     tmp_keys  = (unsigned long long*)(ws + off_keys);
+    uint32_t* tmp_vals  = (uint32_t*)(ws + off_vals);
+    const size_t tiles  = (bound + kSortTile - 1) / kSortTile;
+    uint32_t*    ticket = ctx->d_scalars + LCGS_SCALAR_SORT_TICKET;
+
+    // zero histograms + look-back status (contiguous) and the tickets
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ws, 0, off_status + (size_t)info.num_passes * tiles * kRadix * sizeof(uint32_t), s));
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, kMaxSortPasses * sizeof(uint32_t), s));
+
+    radix_histogram_kernel<<<grid_stride_blocks, 256, 0, s>>>(kin, n_host, d_n, capacity, hist, info);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+
+    const unsigned sweep_blocks = (unsigned)(tiles < (size_t)ctx->num_sms * 2 ? tiles : (size_t)ctx->num_sms * 2);
+    const unsigned long long* src_k = kin;
+    const uint32_t*           src_v = vals_in;
+    for (int p = 0; p < info.num_passes; p++) {
+        const bool          to_out = ((info.num_passes - 1 - p) % 2) == 0;
+        unsigned long long* dst_k  = to_out ? kout : tmp_keys;
+        uint32_t*           dst_v  = to_out ? vals_out : tmp_vals;
+        onesweep_pass_kernel<<<sweep_blocks, kSortThreads, 0, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
+                                                                  hist + p * kRadix, status + (size_t)p * tiles * kRadix,
+                                                                  ticket + p, info.shift[p], info.mask[p]);
+        LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+        src_k = dst_k;
+        src_v = dst_v;
+    }
+    return LCGS_B200_OK;
+}
+
+}  // namespace lcgs_b200

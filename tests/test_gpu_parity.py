@@ -1,0 +1,289 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): visibility masks, tile counts, sorted keys and tile ranges
+bit-exact; rendered RGB within max-abs 2e-3 per channel and PSNR >= 50 dB.  We additionally hold
+depth / pixel means / conic / colour / radii / offsets / unsorted lists / sorted values bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from luisacomputegaussiansplatting_b200 import scenes
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS = 2e-3
+MIN_PSNR = 50.0
+
+
+@pytest.fixture(scope="module")
+def lcgs():
+    from luisacomputegaussiansplatting_b200 import lcgs as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def dev(lcgs):
+    d = lcgs.Device(0)
+    yield d
+    d.close()
+
+
+def psnr(a, b):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return math.inf if mse == 0 else 10.0 * math.log10(1.0 / mse)
+
+
+def assert_image_close(got, want):
+    err = float(np.abs(got - want).max())
+    p = psnr(got, want)
+    assert err <= MAX_ABS, "max-abs %.3g" % err
+    assert p >= MIN_PSNR, "psnr %.2f" % p
+    return err, p
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_frame_matches(gpu: dict, fr: "orc.Frame", fused: bool):
+    n = fr.num_rendered
+    assert gpu["num_rendered"] == n
+    assert np.array_equal(bits(gpu["depth"]) , bits(fr.depth)), "depth / visibility mask"
+    assert np.array_equal(gpu["depth"] >= 0.2, fr.depth >= 0.2)
+    assert np.array_equal(gpu["radii"], fr.radii), "radii"
+    assert np.array_equal(gpu["tiles_touched"], fr.tiles_touched), "tile counts"
+    assert np.array_equal(bits(gpu["means_2d"]), bits(fr.means_2d)), "pixel means"
+    assert np.array_equal(bits(gpu["conic"]), bits(fr.conic)), "conic"
+    sel = fr.tiles_touched > 0 if fused else np.ones_like(fr.tiles_touched, bool)
+    assert np.array_equal(bits(gpu["color"][sel]), bits(fr.color[sel])), "colour"
+    assert np.array_equal(gpu["offsets"], fr.offsets), "inclusive sum"
+    assert np.array_equal(gpu["keys_unsorted"], fr.keys_unsorted), "unsorted keys"
+    assert np.array_equal(gpu["vals_unsorted"], fr.vals_unsorted), "unsorted values"
+    assert np.array_equal(gpu["keys_sorted"], fr.keys_sorted), "sorted keys"
+    assert np.array_equal(gpu["vals_sorted"], fr.vals_sorted), "sorted values (stability)"
+    assert np.array_equal(gpu["ranges"], fr.ranges), "tile ranges"
+    return assert_image_close(gpu["img"], fr.img)
+
+
+def make_case(key, P, W, H, pose=None):
+    sc, cfg = scenes.make_config_scene(key, P=P)
+    if pose is None:
+        pose = (scenes.CAM_POS, scenes.CAM_TARGET, scenes.world_up(cfg.world))
+    return sc, pose
+
+
+CASES = [
+    ("C3", 20_000, 640, 360),     # both dims multiples of 8 but H not of 16
+    ("C1", 10_000, 200, 200),     # blender world, ragged tiles
+    ("C2", 50_000, 1237, 822),    # the bicycle resolution (odd sizes)
+    ("C3", 3_000, 97, 61),        # tiny ragged frame
+    ("C3", 1, 64, 64),            # single Gaussian
+    ("C3", 4097, 320, 240),       # one more than a scan tile
+]
+
+
+@pytest.mark.parametrize("key,P,W,H", CASES)
+def test_fused_render_matches_oracle(lcgs, dev, key, P, W, H):
+    sc, pose = make_case(key, P, W, H)
+    cam = lcgs.make_camera(*pose, W, H)
+    vp = lcgs.view_params(cam)
+    fr = orc.forward(sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, orc.view_params(orc.make_camera(*pose, W, H)))
+    r = lcgs.Renderer(dev, sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, W, H, list_capacity=max(fr.num_rendered, 1) + 17)
+    n = r.render(cam)
+    assert bytes(vp) == bytes(orc.view_params(orc.make_camera(*pose, W, H)))
+    assert_frame_matches(r.intermediates(n), fr, fused=True)
+    # a second frame through the same context/buffers gives the same bits (no stale state)
+    img1 = r.image().cpu().numpy().copy()
+    assert r.render(cam) == n
+    assert np.array_equal(bits(r.image().cpu().numpy()), bits(img1))
+
+
+def test_reference_style_api_matches_oracle(lcgs, dev):
+    """SHProcessor.process + GSProjector.forward + GSTileSplatter.forward, as app/main.cpp:266-299."""
+    import torch
+    W, H, P = 512, 288, 30_000
+    sc, pose = make_case("C3", P, W, H)
+    cam = lcgs.make_camera(*pose, W, H)
+    fr = orc.forward(sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, orc.view_params(orc.make_camera(*pose, W, H)))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    d_pos, d_scale, d_rotq, d_sh, d_opacity = t(sc.pos), t(sc.scale), t(sc.rotq), t(sc.sh), t(sc.opacity)
+    d_color = dev.create_buffer(torch.float32, 3 * P)
+    d_means, d_depth, d_cov = (dev.create_buffer(torch.float32, k * P) for k in (2, 1, 3))
+    L = fr.num_rendered + 100
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    accel = lcgs.GSTileSplatterAccelProxy(
+        dev.create_buffer(torch.int32, P), dev.create_buffer(torch.int32, P), dev.create_buffer(torch.int64, L),
+        dev.create_buffer(torch.int32, L), dev.create_buffer(torch.int64, L), dev.create_buffer(torch.int32, L),
+        dev.create_buffer(torch.int32, 2 * gx * gy))
+    d_img = dev.create_buffer(torch.float32, 3 * W * H)
+    d_radii = dev.create_buffer(torch.int32, P)
+
+    shp, proj, spl = lcgs.SHProcessor(), lcgs.GSProjector(), lcgs.GSTileSplatter()
+    shp.create(dev), proj.create(dev), spl.create(dev)
+    bf, scan, sort = lcgs.BufferFiller(), lcgs.DeviceScan(), lcgs.DeviceRadixSort()
+    scan.create(dev), sort.create(dev)
+    spl.set_buffer_filler(bf), spl.set_device_scan(scan), spl.set_device_radix_sort(sort)
+
+    shp.process(None, lcgs.GPUPointsProxy(P, 3, d_pos), cam, d_sh, d_color, 3, 3)
+    proj.forward(None, lcgs.GSProjectorInputProxy(P, d_pos, d_scale, d_rotq, 1.0),
+                 lcgs.GSProjectorOutputProxy(d_means, d_cov, d_depth), cam)
+    # after K1/K2: colours for every Gaussian, NDC means and pixel^2 covariances
+    o_ndc, o_depth, o_cov = orc.project(sc.pos, sc.scale, sc.rotq, orc.view_params(orc.make_camera(*pose, W, H)))
+    assert np.array_equal(bits(d_color.cpu().numpy().reshape(-1, 3)), bits(fr.color))
+    assert np.array_equal(bits(d_means.cpu().numpy().reshape(-1, 2)), bits(o_ndc))
+    assert np.array_equal(bits(d_cov.cpu().numpy().reshape(-1, 3)), bits(o_cov))
+    assert np.array_equal(bits(d_depth.cpu().numpy()), bits(o_depth))
+
+    inp = lcgs.GSTileSplatterInputProxy(P, (0.0, 0.0, 0.0), d_means, d_depth, d_cov, d_color, d_opacity)
+    out = lcgs.GSSplatForwardOutputProxy(H, W, d_img, d_radii)
+    n = spl.forward(dev, None, accel, inp, out)
+    u32 = lambda x: x.cpu().numpy().view(np.uint32)  # noqa: E731
+    gpu = dict(num_rendered=n, depth=d_depth.cpu().numpy(), means_2d=d_means.cpu().numpy().reshape(-1, 2),
+               conic=d_cov.cpu().numpy().reshape(-1, 3), color=d_color.cpu().numpy().reshape(-1, 3),
+               tiles_touched=u32(accel.tiles_touched), radii=d_radii.cpu().numpy(), offsets=u32(accel.point_offsets),
+               keys_unsorted=accel.point_list_keys_unsorted[:n].cpu().numpy().view(np.uint64),
+               vals_unsorted=u32(accel.point_list_unsorted[:n]),
+               keys_sorted=accel.point_list_keys[:n].cpu().numpy().view(np.uint64),
+               vals_sorted=u32(accel.point_list[:n]), ranges=u32(accel.ranges).reshape(-1, 2),
+               img=d_img.cpu().numpy().reshape(3, H, W))
+    assert_frame_matches(gpu, fr, fused=False)
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2])
+def test_lower_sh_degrees(lcgs, dev, deg):
+    import torch
+    sc, pose = make_case("C3", 5000, 64, 64)
+    cam = lcgs.make_camera(*pose, 64, 64)
+    sh = np.ascontiguousarray(sc.sh[:, :(deg + 1) ** 2, :])
+    want = orc.sh_process(sc.pos, sh, list(cam.position), deg)
+    d_color = dev.create_buffer(torch.float32, 3 * 5000)
+    p = lcgs.SHProcessor()
+    p.create(dev)
+    p.process(None, lcgs.GPUPointsProxy(5000, 3, torch.from_numpy(sc.pos).cuda()), cam, torch.from_numpy(sh).cuda(),
+              d_color, deg, 3)
+    assert np.array_equal(bits(d_color.cpu().numpy().reshape(-1, 3)), bits(want))
+
+
+def test_tile_row_bands_reassemble_the_frame(lcgs, dev):
+    W, H, P = 640, 360, 20_000
+    sc, pose = make_case("C3", P, W, H)
+    cam = lcgs.make_camera(*pose, W, H)
+    ovp = orc.view_params(orc.make_camera(*pose, W, H))
+    full = orc.forward(sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, ovp)
+    gy = (H + 15) // 16
+    img = np.zeros_like(full.img)
+    total = 0
+    for r0, r1 in [(0, 7), (7, 8), (8, gy)]:
+        band = orc.forward(sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, ovp, row0=r0, row1=r1)
+        r = lcgs.Renderer(dev, sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, W, H,
+                          list_capacity=max(band.num_rendered, 1), tile_rows=(r0, r1))
+        n = r.render(cam)
+        assert_frame_matches(r.intermediates(n), band, fused=True)
+        total += n
+        img[:, r0 * 16:min(H, r1 * 16)] = r.image().cpu().numpy()[:, r0 * 16:min(H, r1 * 16)]
+    assert total == full.num_rendered
+    assert_image_close(img, full.img)
+
+
+def test_empty_frame_and_capacity_overflow(lcgs, dev):
+    W, H, P = 128, 96, 2000
+    sc, pose = make_case("C3", P, W, H)
+    cam = lcgs.make_camera(*pose, W, H)
+    # everything behind the camera: num_rendered == 0 and the image is left untouched (Q10)
+    behind = sc.pos.copy()
+    behind[:] = np.array(scenes.CAM_POS, np.float32) - 5.0 * np.array(list(cam.front), np.float32)
+    r = lcgs.Renderer(dev, behind, sc.scale, sc.rotq, sc.sh, sc.opacity, W, H, list_capacity=1000)
+    r.img.fill_(0.25)
+    assert r.render(cam) == 0
+    assert bool((r.img == 0.25).all())
+    # overflow is reported, not undefined behaviour (reference: unchecked, main.cpp:245)
+    fr = orc.forward(sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, orc.view_params(orc.make_camera(*pose, W, H)))
+    assert fr.num_rendered > 64
+    r2 = lcgs.Renderer(dev, sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, W, H, list_capacity=64)
+    with pytest.raises(lcgs.CapacityError):
+        r2.render(cam)
+    # and the context stays usable
+    r3 = lcgs.Renderer(dev, sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, W, H, list_capacity=fr.num_rendered)
+    assert r3.render(cam) == fr.num_rendered
+    assert_image_close(r3.image().cpu().numpy(), fr.img)
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4095, 4096, 4097, 100_003, 3_000_000])
+def test_scan_primitive(lcgs, dev, n):
+    import torch
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 50, size=n, dtype=np.uint32)
+    d_in = torch.from_numpy(x.view(np.int32)).cuda()
+    d_out = torch.zeros(n, dtype=torch.int32, device="cuda")
+    s = lcgs.DeviceScan()
+    s.create(dev)
+    s.InclusiveSum(None, d_in, d_out, n)
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), np.cumsum(x, dtype=np.uint64).astype(np.uint32))
+
+
+def test_scan_wraps_like_uint32(lcgs, dev):
+    import torch
+    x = np.full(10_000, 0x7FFFFFF, np.uint32)
+    d_in = torch.from_numpy(x.view(np.int32)).cuda()
+    d_out = torch.zeros_like(d_in)
+    s = lcgs.DeviceScan()
+    s.create(dev)
+    s.InclusiveSum(None, d_in[1:], d_out[1:], 9_999)  # also an unaligned (4-byte offset) view
+    want = np.cumsum(x[1:], dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(d_out[1:].cpu().numpy().view(np.uint32), want)
+
+
+@pytest.mark.parametrize("n,bits_range,key_bits", [(0, (0, 64), 64), (1, (0, 64), 64), (255, (0, 64), 64),
+                                                   (4096, (0, 64), 64), (4097, (0, 64), 64), (100_003, (0, 45), 45),
+                                                   (1_000_000, (0, 64), 64), (2_000_000, (0, 44), 44),
+                                                   (300_000, (8, 40), 64), (50_000, (0, 3), 64)])
+def test_sort_primitive(lcgs, dev, n, bits_range, key_bits):
+    import torch
+    rng = np.random.default_rng(n + 1)
+    keys = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64)
+    if key_bits < 64:
+        keys &= np.uint64((1 << key_bits) - 1)
+    if n > 10:  # plenty of duplicate keys to exercise stability
+        keys[rng.integers(0, n, n // 3)] = keys[rng.integers(0, n, n // 3)]
+    vals = np.arange(n, dtype=np.uint32)
+    d_k = torch.from_numpy(keys.view(np.int64)).cuda()
+    d_v = torch.from_numpy(vals.view(np.int32)).cuda()
+    d_ko, d_vo = torch.zeros_like(d_k), torch.zeros_like(d_v)
+    s = lcgs.DeviceRadixSort()
+    s.create(dev)
+    s.SortPairs(None, d_k, d_ko, d_v, d_vo, n, *bits_range)
+    b, e = bits_range
+    mask = np.uint64(((1 << (e - b)) - 1) << b) if e - b < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+    order = np.argsort(keys & mask, kind="stable")
+    assert np.array_equal(d_ko.cpu().numpy().view(np.uint64), keys[order])
+    assert np.array_equal(d_vo.cpu().numpy().view(np.uint32), vals[order])
+    # inputs are preserved
+    assert np.array_equal(d_k.cpu().numpy().view(np.uint64), keys)
+
+
+def test_sorted_input_and_all_equal_keys(lcgs, dev):
+    import torch
+    s = lcgs.DeviceRadixSort()
+    s.create(dev)
+    for keys in (np.arange(70_000, dtype=np.uint64) << np.uint64(20), np.full(70_000, 12345, np.uint64),
+                 (np.arange(70_000, dtype=np.uint64)[::-1] << np.uint64(33)).copy()):
+        vals = np.arange(keys.size, dtype=np.uint32)
+        d_k, d_v = torch.from_numpy(keys.view(np.int64)).cuda(), torch.from_numpy(vals.view(np.int32)).cuda()
+        d_ko, d_vo = torch.zeros_like(d_k), torch.zeros_like(d_v)
+        s.SortPairs(None, d_k, d_ko, d_v, d_vo, keys.size)
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(d_ko.cpu().numpy().view(np.uint64), keys[order])
+        assert np.array_equal(d_vo.cpu().numpy().view(np.uint32), vals[order])
+
+
+def test_buffer_filler(lcgs, dev):
+    import torch
+    bf = lcgs.BufferFiller()
+    a = torch.zeros(100_001, dtype=torch.int32, device="cuda")
+    b = torch.zeros(33, dtype=torch.int64, device="cuda")
+    c = torch.zeros(7, dtype=torch.float32, device="cuda")
+    bf.fill(dev, a, 7), bf.fill(dev, b, 1 << 40), bf.fill(dev, c, 0.5)
+    assert bool((a == 7).all()) and bool((b == (1 << 40)).all()) and bool((c == 0.5).all())
