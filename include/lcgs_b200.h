@@ -239,6 +239,9 @@ LCGS_B200_API int lcgs_b200_read_image(lcgs_b200_ctx* ctx, const lcgs_b200_frame
 LCGS_B200_API int lcgs_b200_set_profiling(lcgs_b200_ctx* ctx, int enabled);
 /* Synchronises; ms[i] = device time of stage i of the last whole-frame call. */
 LCGS_B200_API int lcgs_b200_stage_times(lcgs_b200_ctx* ctx, float ms[LCGS_B200_NUM_STAGES]);
+/* Synchronises; device time of the last profiled sort split into its histogram kernel and its
+ * `num_passes` onesweep launches (passes_ms / num_passes = average launch duration). */
+LCGS_B200_API int lcgs_b200_sort_breakdown(lcgs_b200_ctx* ctx, float* histogram_ms, float* passes_ms, int* num_passes);
 
 #ifdef __cplusplus
 }

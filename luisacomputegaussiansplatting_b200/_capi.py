@@ -89,6 +89,7 @@ _PROTOS = {
     "lcgs_b200_read_image": (_I, [_VP, C.POINTER(Frame), _VP, _VP]),
     "lcgs_b200_set_profiling": (_I, [_VP, _I]),
     "lcgs_b200_stage_times": (_I, [_VP, C.POINTER(_F)]),
+    "lcgs_b200_sort_breakdown": (_I, [_VP, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I)]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 

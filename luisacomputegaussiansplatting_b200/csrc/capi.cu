@@ -193,6 +193,8 @@ int lcgs_b200_ctx_destroy(lcgs_b200_ctx* ctx)
     if (ctx->record_ws.ptr) cudaFree(ctx->record_ws.ptr);
     for (int i = 0; i < 16; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 3; i++)
+        if (ctx->ev_sort[i]) cudaEventDestroy(ctx->ev_sort[i]);
     delete ctx;
     return LCGS_B200_OK;
 }
@@ -497,8 +499,25 @@ int lcgs_b200_set_profiling(lcgs_b200_ctx* ctx, int enabled)
     if (enabled)
         for (int i = 0; i < 16; i++)
             if (!ctx->ev[i]) LCGS_CUDA_CHECK(ctx, cudaEventCreate(&ctx->ev[i]));
-    ctx->profiling = enabled ? 1 : 0;
-    ctx->ev_valid  = 0;
+    if (enabled)
+        for (int i = 0; i < 3; i++)
+            if (!ctx->ev_sort[i]) LCGS_CUDA_CHECK(ctx, cudaEventCreate(&ctx->ev_sort[i]));
+    ctx->profiling     = enabled ? 1 : 0;
+    ctx->ev_valid      = 0;
+    ctx->ev_sort_valid = 0;
+    return LCGS_B200_OK;
+}
+
+int lcgs_b200_sort_breakdown(lcgs_b200_ctx* ctx, float* histogram_ms, float* passes_ms, int* num_passes)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, histogram_ms && passes_ms && num_passes, "sort_breakdown: null pointer");
+    LCGS_REQUIRE(ctx, ctx->ev_sort_valid, "sort_breakdown: no profiled sort (enable profiling first)");
+    LCGS_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->ev_sort[2]));
+    LCGS_CUDA_CHECK(ctx, cudaEventElapsedTime(histogram_ms, ctx->ev_sort[0], ctx->ev_sort[1]));
+    LCGS_CUDA_CHECK(ctx, cudaEventElapsedTime(passes_ms, ctx->ev_sort[1], ctx->ev_sort[2]));
+    *num_passes = ctx->sort_passes;
     return LCGS_B200_OK;
 }
 

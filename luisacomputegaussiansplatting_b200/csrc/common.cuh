@@ -56,7 +56,9 @@ struct lcgs_b200_ctx {
     cudaEvent_t  ev[16];
     int          ev_count   = 0;
     int          ev_valid   = 0;
-    cudaEvent_t  done_event = nullptr;
+    cudaEvent_t  ev_sort[3] = { nullptr, nullptr, nullptr };  // before histogram, before passes, after passes
+    int          sort_passes = 0;
+    int          ev_sort_valid = 0;
 };
 
 #define LCGS_SCALAR_NUM_RENDERED 0

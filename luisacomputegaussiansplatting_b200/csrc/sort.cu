@@ -310,8 +310,11 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ws, 0, off_status + (size_t)info.num_passes * tiles * kRadix * sizeof(uint32_t), s));
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, kMaxSortPasses * sizeof(uint32_t), s));
 
+    const bool prof = ctx->profiling && ctx->ev_sort[0];
+    if (prof) cudaEventRecord(ctx->ev_sort[0], s);
     radix_histogram_kernel<<<grid_stride_blocks, 256, 0, s>>>(kin, n_host, d_n, capacity, hist, info);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    if (prof) cudaEventRecord(ctx->ev_sort[1], s);
 
     const unsigned sweep_blocks = (unsigned)(tiles < (size_t)ctx->num_sms * 2 ? tiles : (size_t)ctx->num_sms * 2);
     const unsigned long long* src_k = kin;
@@ -326,6 +329,11 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
         LCGS_CUDA_CHECK(ctx, cudaGetLastError());
         src_k = dst_k;
         src_v = dst_v;
+    }
+    if (prof) {
+        cudaEventRecord(ctx->ev_sort[2], s);
+        ctx->sort_passes   = info.num_passes;
+        ctx->ev_sort_valid = 1;
     }
     return LCGS_B200_OK;
 }

@@ -125,6 +125,11 @@ class Device:
         self.check(self.lib.lcgs_b200_stage_times(self.ctx, ms))
         return dict(zip(_capi.STAGES, [float(x) for x in ms]))
 
+    def sort_breakdown(self) -> dict:
+        h, p, k = C.c_float(), C.c_float(), C.c_int()
+        self.check(self.lib.lcgs_b200_sort_breakdown(self.ctx, C.byref(h), C.byref(p), C.byref(k)))
+        return dict(histogram_ms=h.value, passes_ms=p.value, num_passes=k.value)
+
     def num_rendered(self, stream: Optional[torch.cuda.Stream] = None) -> int:
         n = C.c_int()
         self.check(self.lib.lcgs_b200_num_rendered(self.ctx, _stream_handle(stream), C.byref(n)))
