@@ -70,5 +70,38 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+APP_DIR = os.path.join(HERE, "cpp", "app")
+APP_BIN = os.path.join(HERE, "lcgs-app")
+APP_SOURCES = [os.path.join(APP_DIR, "main.cpp"), os.path.join(APP_DIR, "gaussians.cpp")]
+APP_INCLUDES = [os.path.join(HERE, "cpp", "include"), os.path.join(HERE, "..", "include"), APP_DIR,
+                "/usr/local/cuda/include"]
+
+
+def _app_deps():
+    deps = list(APP_SOURCES)
+    for root, _, files in os.walk(os.path.join(HERE, "cpp")):
+        deps += [os.path.join(root, f) for f in files if f.endswith((".h", ".hpp"))]
+    return deps
+
+
+def build_app(force: bool = False) -> str:
+    """lcgs-app: the C++ CLI (cpp/app) over the C++ facade (cpp/include) and liblcgs_b200.so."""
+    lib = build_native()
+    newest = max([_mtime(f) for f in _app_deps()] + [_mtime(lib)])
+    if not force and _mtime(APP_BIN) >= newest:
+        return APP_BIN
+    cmd = ["g++", "-O2", "-std=c++20", "-Wall", "-Wextra", "-Wno-missing-field-initializers"]
+    for inc in APP_INCLUDES:
+        cmd += ["-I", inc]
+    cmd += APP_SOURCES + ["-o", APP_BIN, "-L", HERE, "-llcgs_b200", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64",
+                          "-lcudart_static", "-lz", "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("building lcgs-app failed")
+    return APP_BIN
+
+
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose=True))
+    print(build_app(force="--force" in sys.argv))

@@ -379,4 +379,53 @@ LCGS_HD float alpha_threshold(float op)
     return bits_float(lo);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Conservative rectangle culling for the blend kernel.
+//
+// power(d) = a*dx^2 + b*dx*dy + c*dy^2 with d = mean - pixel, (a,b,c) = (-0.5*conic.x, -conic.y,
+// -0.5*conic.z).  blend_power() is the canonical per-pixel evaluation (shared with the oracle).
+// cull_rect() returns true only if NO pixel centre inside [x0,x1]x[y0,y1] can satisfy
+// power >= thr, i.e. every such pair would be skipped by the alpha test anyway
+// (gs_tile_splatter/shader.cpp:259), so dropping the Gaussian for that rectangle changes nothing.
+// It maximises the (concave) quadratic over the rectangle exactly -- the maximiser lies on one of
+// the at most two edges facing the mean -- and adds a margin that covers the rounding error of the
+// per-pixel float evaluation (<= ~1e-6 * (|a|dx^2 + |c|dy^2)).
+// ---------------------------------------------------------------------------------------------
+LCGS_HD float blend_power(float a, float b, float c, float dx, float dy)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(b * dx, dy, __fmaf_rn(a * dx, dx, (c * dy) * dy));
+#else
+    return fmaf(b * dx, dy, fmaf(a * dx, dx, (c * dy) * dy));
+#endif
+}
+
+LCGS_HD bool cull_rect(float mx, float my, float a, float b, float c, float thr, float x0, float y0, float x1, float y1)
+{
+    if (!(thr <= 0.0f)) return thr > 0.0f;  // +inf: nothing ever passes; NaN: keep
+    // only a strictly concave form is culled; anything degenerate is kept
+    if (!(a < 0.0f && c < 0.0f && 4.0f * a * c - b * b > 0.0f)) return false;
+    const float dxl = mx - x1, dxh = mx - x0;  // dx ranges over [dxl, dxh]
+    const float dyl = my - y1, dyh = my - y0;
+    const bool  in_x = dxl <= 0.0f && dxh >= 0.0f;
+    const bool  in_y = dyl <= 0.0f && dyh >= 0.0f;
+    if (in_x && in_y) return false;  // the mean is inside: power reaches 0
+    float pmax = -INFINITY;
+    if (!in_x) {
+        const float xe = dxl > 0.0f ? dxl : dxh;  // edge facing the mean
+        float       dy = -(b * xe) / (2.0f * c);
+        dy             = fminf(fmaxf(dy, dyl), dyh);
+        pmax           = fmaxf(pmax, (a * xe) * xe + (b * xe) * dy + (c * dy) * dy);
+    }
+    if (!in_y) {
+        const float ye = dyl > 0.0f ? dyl : dyh;
+        float       dx = -(b * ye) / (2.0f * a);
+        dx             = fminf(fmaxf(dx, dxl), dxh);
+        pmax           = fmaxf(pmax, (a * dx) * dx + (b * dx) * ye + (c * ye) * ye);
+    }
+    const float ex = fmaxf(dxl * dxl, dxh * dxh), ey = fmaxf(dyl * dyl, dyh * dyh);
+    const float margin = 4e-6f * (-(a * ex) - (c * ey)) + 1e-6f;
+    return pmax + margin < thr;
+}
+
 }  // namespace lcgs_b200

@@ -92,19 +92,31 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 // ---- one onesweep pass -------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSortThreads, 2)
+// Shared memory (dynamic, 59.4 KB -> three CTAs per SM):
+//   s_warp_hist [8][256] u32   per-warp digit counters, then exclusive prefix over warps
+//   s_keys      [4096]   u64   tile's keys in tile-sorted order
+//   s_vals      [4096]   u32   tile's values in tile-sorted order
+//   s_tile_start[256]    u32   exclusive digit prefix inside the tile
+//   s_digit_base[256]    u32   global base of the digit minus s_tile_start
+constexpr size_t kSweepSmemBytes = (size_t)(kSortThreads / 32) * kRadix * 4 + (size_t)kSortTile * 8 + (size_t)kSortTile * 4 +
+                                   (size_t)kRadix * 4 * 2 + 64;
+constexpr int kLookbackWindow = 4;
+
+__global__ void __launch_bounds__(kSortThreads, 3)
     onesweep_pass_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
                          const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
                          const uint32_t* __restrict__ d_n, size_t capacity, const uint32_t* __restrict__ hist /* [256] */,
                          uint32_t* status /* [tiles][256] */, uint32_t* ticket, int shift, uint32_t mask)
 {
-    __shared__ uint32_t           s_warp_hist[(kSortThreads / 32) * kRadix];  // per-warp digit counters
-    __shared__ unsigned long long s_keys[kSortTile];                          // aliased by the values later
-    __shared__ uint32_t           s_tile_start[kRadix];   // exclusive digit prefix inside the tile
-    __shared__ uint32_t           s_digit_base[kRadix];   // global base of the digit minus s_tile_start
-    __shared__ uint32_t           s_scan[8];
-    __shared__ uint32_t           s_tile;
-    uint32_t* const s_vals = reinterpret_cast<uint32_t*>(s_keys);
+    static_assert(kSortThreads == kRadix, "one thread per digit");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* const s_keys       = reinterpret_cast<unsigned long long*>(smem_raw);
+    uint32_t* const           s_vals       = reinterpret_cast<uint32_t*>(s_keys + kSortTile);
+    uint32_t* const           s_warp_hist  = s_vals + kSortTile;
+    uint32_t* const           s_tile_start = s_warp_hist + (kSortThreads / 32) * kRadix;
+    uint32_t* const           s_digit_base = s_tile_start + kRadix;
+    uint32_t* const           s_scan       = s_digit_base + kRadix;  // [8]
+    uint32_t* const           s_tile_slot  = s_scan + 8;
 
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL    = 0xFFFFFFFFu;
@@ -117,36 +129,26 @@ __global__ void __launch_bounds__(kSortThreads, 2)
 
     for (;;) {
         __syncthreads();  // previous iteration finished with shared memory
-        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        if (tid == 0) *s_tile_slot = atomicAdd(ticket, 1u);
         for (int k = tid; k < (kSortThreads / 32) * kRadix; k += kSortThreads) s_warp_hist[k] = 0u;
         __syncthreads();
-        const uint32_t tile = s_tile;
+        const uint32_t tile = *s_tile_slot;
         if (tile >= num_tiles) break;
         const size_t   tile_base = (size_t)tile * kSortTile;
         const uint32_t nvalid    = (uint32_t)((n - tile_base) < (size_t)kSortTile ? (n - tile_base) : (size_t)kSortTile);
+        const uint32_t q0        = warp * (kSortItems * 32) + lane;  // warp-striped: item j sits at q0 + 32*j
 
-        // ---- load (warp-striped: item j of lane l sits at warp*512 + j*32 + l) ----------------
+        // ---- load keys ------------------------------------------------------------------------
         unsigned long long key[kSortItems];
-        uint32_t           val[kSortItems];
 #pragma unroll
-        for (int j = 0; j < kSortItems; j++) {
-            const uint32_t q = warp * (kSortItems * 32) + j * 32 + lane;
-            if (q < nvalid) {
-                key[j] = __ldg(keys_in + tile_base + q);
-                val[j] = __ldg(vals_in + tile_base + q);
-            } else {
-                key[j] = ~0ull;
-                val[j] = 0u;
-            }
-        }
+        for (int j = 0; j < kSortItems; j++) key[j] = (q0 + 32 * j < nvalid) ? __ldg(keys_in + tile_base + q0 + 32 * j) : ~0ull;
 
         // ---- rank inside the warp with match_any ---------------------------------------------
         uint32_t  rank[kSortItems];
         uint32_t* my_hist = s_warp_hist + warp * kRadix;
 #pragma unroll
         for (int j = 0; j < kSortItems; j++) {
-            const uint32_t q     = warp * (kSortItems * 32) + j * 32 + lane;
-            const bool     valid = q < nvalid;
+            const bool     valid = q0 + 32 * j < nvalid;
             const uint32_t d     = valid ? (uint32_t)((key[j] >> shift) & mask) : (uint32_t)kRadix;
             const unsigned peers = __match_any_sync(FULL, d);
             const unsigned lower = peers & lt_mask;
@@ -159,28 +161,55 @@ __global__ void __launch_bounds__(kSortThreads, 2)
         }
         __syncthreads();
 
-        // ---- per digit (thread d): prefix over warps, tile histogram, look-back ----------------
+        // ---- per digit (thread d): prefix over warps, tile histogram, early publish ------------
         uint32_t tile_count = 0;
 #pragma unroll
         for (int w = 0; w < kSortThreads / 32; w++) {
-            const uint32_t c           = s_warp_hist[w * kRadix + tid];
+            const uint32_t c              = s_warp_hist[w * kRadix + tid];
             s_warp_hist[w * kRadix + tid] = tile_count;
             tile_count += c;
         }
+        uint32_t* const my_status = status + (size_t)tile * kRadix + tid;
+        if (tile > 0) st_relaxed_u32(my_status, kStatusAggregate | tile_count);
         const uint32_t tile_start = block_exclusive_scan_256(tile_count, s_scan, nullptr);
         s_tile_start[tid]         = tile_start;
+        __syncthreads();
+
+        // ---- scatter keys into shared memory in tile-sorted order; start the value loads --------
+#pragma unroll
+        for (int j = 0; j < kSortItems; j++) {
+            if (q0 + 32 * j < nvalid) {
+                const uint32_t d = (uint32_t)((key[j] >> shift) & mask);
+                rank[j] += s_tile_start[d] + my_hist[d];
+                s_keys[rank[j]] = key[j];
+            }
+        }
+        uint32_t val[kSortItems];
+#pragma unroll
+        for (int j = 0; j < kSortItems; j++) val[j] = (q0 + 32 * j < nvalid) ? __ldg(vals_in + tile_base + q0 + 32 * j) : 0u;
+
+        // ---- decoupled look-back, kLookbackWindow predecessors in flight at a time --------------
         {
-            uint32_t* my_status = status + (size_t)tile * kRadix + tid;
-            uint32_t  prefix    = 0;
+            uint32_t prefix = 0;
             if (tile > 0) {
-                st_relaxed_u32(my_status, kStatusAggregate | tile_count);
-                const uint32_t* p = my_status - kRadix;
-                for (;;) {
-                    uint32_t st;
-                    do { st = ld_relaxed_u32(p); } while ((st >> 30) == 0u);
-                    prefix += st & kStatusValueMask;
-                    if ((st >> 30) == 2u) break;
-                    p -= kRadix;
+                int  p    = (int)tile - 1;
+                bool more = true;
+                while (more) {
+                    uint32_t st[kLookbackWindow];
+#pragma unroll
+                    for (int k = 0; k < kLookbackWindow; k++)
+                        st[k] = (p - k >= 0) ? ld_relaxed_u32(status + (size_t)(p - k) * kRadix + tid) : kStatusInclusive;
+#pragma unroll
+                    for (int k = 0; k < kLookbackWindow; k++) {
+                        if (!more) break;
+                        if ((st[k] >> 30) == 0u) {  // not published yet: poll again from this tile
+                            p -= k;
+                            break;
+                        }
+                        prefix += st[k] & kStatusValueMask;
+                        if ((st[k] >> 30) == 2u) more = false;
+                        else if (k == kLookbackWindow - 1) p -= kLookbackWindow;
+                    }
                 }
             }
             st_relaxed_u32(my_status, kStatusInclusive | ((prefix + tile_count) & kStatusValueMask));
@@ -188,43 +217,23 @@ __global__ void __launch_bounds__(kSortThreads, 2)
         }
         __syncthreads();
 
-        // ---- scatter keys into shared memory in tile-sorted order -----------------------------
-#pragma unroll
-        for (int j = 0; j < kSortItems; j++) {
-            const uint32_t q = warp * (kSortItems * 32) + j * 32 + lane;
-            if (q < nvalid) {
-                const uint32_t d = (uint32_t)((key[j] >> shift) & mask);
-                rank[j] += s_tile_start[d] + my_hist[d];
-                s_keys[rank[j]] = key[j];
-            }
-        }
-        __syncthreads();
-
-        // ---- coalesced key write-out; remember each slot's global destination -----------------
-        uint32_t dst[kSortItems];
+        // ---- coalesced key write-out; scatter the values -----------------------------------------
 #pragma unroll
         for (int j = 0; j < kSortItems; j++) {
             const uint32_t q = tid + j * kSortThreads;
             if (q < nvalid) {
                 const unsigned long long k = s_keys[q];
-                const uint32_t           d = (uint32_t)((k >> shift) & mask);
-                dst[j]                     = s_digit_base[d] + q;
-                keys_out[dst[j]]           = k;
+                keys_out[s_digit_base[(uint32_t)((k >> shift) & mask)] + q] = k;
             }
         }
-        __syncthreads();
-
-        // ---- same for the values, through the same shared memory ------------------------------
 #pragma unroll
-        for (int j = 0; j < kSortItems; j++) {
-            const uint32_t q = warp * (kSortItems * 32) + j * 32 + lane;
-            if (q < nvalid) s_vals[rank[j]] = val[j];
-        }
+        for (int j = 0; j < kSortItems; j++)
+            if (q0 + 32 * j < nvalid) s_vals[rank[j]] = val[j];
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < kSortItems; j++) {
             const uint32_t q = tid + j * kSortThreads;
-            if (q < nvalid) vals_out[dst[j]] = s_vals[q];
+            if (q < nvalid) vals_out[s_digit_base[(uint32_t)((s_keys[q] >> shift) & mask)] + q] = s_vals[q];
         }
     }
 }
@@ -316,14 +325,20 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     if (prof) cudaEventRecord(ctx->ev_sort[1], s);
 
-    const unsigned sweep_blocks = (unsigned)(tiles < (size_t)ctx->num_sms * 2 ? tiles : (size_t)ctx->num_sms * 2);
+    static bool smem_attr_set = false;  // opt in to > 48 KB of dynamic shared memory once per process
+    if (!smem_attr_set) {
+        LCGS_CUDA_CHECK(ctx, cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)kSweepSmemBytes));
+        smem_attr_set = true;
+    }
+    const unsigned sweep_blocks = (unsigned)(tiles < (size_t)ctx->num_sms * 3 ? tiles : (size_t)ctx->num_sms * 3);
     const unsigned long long* src_k = kin;
     const uint32_t*           src_v = vals_in;
     for (int p = 0; p < info.num_passes; p++) {
         const bool          to_out = ((info.num_passes - 1 - p) % 2) == 0;
         unsigned long long* dst_k  = to_out ? kout : tmp_keys;
         uint32_t*           dst_v  = to_out ? vals_out : tmp_vals;
-        onesweep_pass_kernel<<<sweep_blocks, kSortThreads, 0, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
+        onesweep_pass_kernel<<<sweep_blocks, kSortThreads, kSweepSmemBytes, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
                                                                   hist + p * kRadix, status + (size_t)p * tiles * kRadix,
                                                                   ticket + p, info.shift[p], info.mask[p]);
         LCGS_CUDA_CHECK(ctx, cudaGetLastError());

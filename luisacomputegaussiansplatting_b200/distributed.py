@@ -1,0 +1,152 @@
+"""Multi-GPU partitioning of the forward render path (one process per GPU, torch.distributed).
+
+The path shards in the two ways BASELINE.json names, with no mid-pipeline exchange:
+
+* view sharding   -- a camera sweep is split by view (view k -> rank k mod G), the Gaussian set is
+                     replicated, every rank runs the whole pipeline on its own GPU; the only
+                     collective gathers the finished frames on rank 0.
+* tile-row sharding -- one very large frame is split into contiguous bands of 16-pixel tile rows;
+                     every rank preprocesses all Gaussians but bins/sorts/blends only its band (the
+                     kernels clip tile rects to the band, so instance sets partition exactly); the
+                     only collective gathers the finished strips on rank 0.
+
+Everything here is host logic over torch.distributed and works with the `nccl` backend (CUDA
+tensors, NVLink) and the `gloo` backend (CPU tensors, used by the CPU tests).  The renderer itself is
+passed in as a callable, so nothing in this file touches a kernel.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+# --------------------------------------------------------------------------------------------------
+# partitioning
+# --------------------------------------------------------------------------------------------------
+
+def shard_views(num_views: int, world: int, rank: int) -> List[int]:
+    """Views of a sweep owned by `rank`: k with k mod world == rank (round-robin keeps neighbouring,
+    similarly expensive views on different GPUs)."""
+    return list(range(rank, num_views, world))
+
+
+def split_tile_rows(num_rows: int, world: int, weights: Optional[Sequence[float]] = None) -> List[Tuple[int, int]]:
+    """Contiguous bands [r0, r1) of tile rows, one per rank, covering [0, num_rows).
+
+    With `weights` (e.g. instances per tile row from a previous frame) the bands are balanced by
+    cumulative weight instead of by row count: tile populations are heavy-tailed.  Bands may be
+    empty when world > num_rows."""
+    if weights is None:
+        weights = [1.0] * num_rows
+    assert len(weights) == num_rows
+    cum = [0.0]
+    for w in weights:
+        cum.append(cum[-1] + max(float(w), 0.0))
+    if cum[-1] <= 0.0:
+        cum = [float(i) for i in range(num_rows + 1)]
+    total = cum[-1]
+    cuts = [0]
+    for g in range(1, world):
+        target = total * g / world
+        r = cuts[-1]
+        while r < num_rows and abs(cum[r + 1] - target) <= abs(cum[r] - target):
+            r += 1
+        cuts.append(r)
+    cuts.append(num_rows)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def row_weights_from_ranges(ranges: torch.Tensor, gx: int) -> List[float]:
+    """Instances per tile row from a frame's ranges buffer ([tiles][2], start/end)."""
+    r = ranges.view(-1, 2).to(torch.int64)
+    per_tile = (r[:, 1] - r[:, 0]).clamp_(min=0)
+    rows = per_tile.numel() // gx
+    return per_tile[: rows * gx].view(rows, gx).sum(dim=1).to(torch.float64).cpu().tolist()
+
+
+# --------------------------------------------------------------------------------------------------
+# collectives (the only exchange steps of the path)
+# --------------------------------------------------------------------------------------------------
+
+def gather_frames(frame: torch.Tensor, dst: int = 0, group=None) -> Optional[List[torch.Tensor]]:
+    """Gather one equally-sized frame per rank on `dst` (NCCL has no native gather; torch lowers this
+    to grouped send/recv).  Returns the list on dst, None elsewhere."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    out = [torch.empty_like(frame) for _ in range(world)] if rank == dst else None
+    dist.gather(frame, out, dst=dst, group=group)
+    return out
+
+
+def gather_strips(img: torch.Tensor, bands: Sequence[Tuple[int, int]], height: int, dst: int = 0,
+                  group=None) -> Optional[torch.Tensor]:
+    """Assemble a tile-row-sharded frame on `dst`.
+
+    `img` is this rank's planar [3, H, W] image of which only pixel rows [16*r0, min(H, 16*r1)) of its
+    band are valid.  Each rank sends its strip (3 contiguous channel chunks packed into one message);
+    dst writes them into its own image and returns it."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    rows = [(min(height, 16 * r0), min(height, 16 * r1)) for r0, r1 in bands]
+    if rank != dst:
+        y0, y1 = rows[rank]
+        if y1 > y0:
+            dist.send(img[:, y0:y1, :].contiguous(), dst=dst, group=group)
+        return None
+    for src in range(world):
+        if src == dst:
+            continue
+        y0, y1 = rows[src]
+        if y1 > y0:
+            buf = torch.empty((3, y1 - y0, img.shape[2]), dtype=img.dtype, device=img.device)
+            dist.recv(buf, src=src, group=group)
+            img[:, y0:y1, :] = buf
+    return img
+
+
+# --------------------------------------------------------------------------------------------------
+# drivers
+# --------------------------------------------------------------------------------------------------
+
+def render_sweep_view_sharded(render_view: Callable[[int], torch.Tensor], num_views: int, dst: int = 0,
+                              group=None) -> Optional[List[torch.Tensor]]:
+    """Render `num_views` views, view k on rank k mod G, and gather them in view order on `dst`.
+
+    `render_view(k)` returns this rank's finished frame for view k (any fixed shape).  Every rank
+    takes part in ceil(num_views / G) gather rounds (ranks without a view in the last round send a
+    dummy frame that dst drops)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = shard_views(num_views, world, rank)
+    rounds = (num_views + world - 1) // world
+    frames: List[Optional[torch.Tensor]] = [None] * num_views if rank == dst else []
+    template = None
+    for i in range(rounds):
+        if i < len(mine):
+            frame = render_view(mine[i])
+            template = frame
+        else:
+            assert template is not None or rounds == 1
+            frame = torch.zeros_like(template) if template is not None else render_view(0) * 0
+        got = gather_frames(frame, dst=dst, group=group)
+        if rank == dst:
+            for r in range(world):
+                k = i * world + r
+                if k < num_views:
+                    frames[k] = got[r].clone()
+    return frames if rank == dst else None
+
+
+def render_frame_tile_row_sharded(render_band: Callable[[int, int], torch.Tensor], height: int,
+                                  weights: Optional[Sequence[float]] = None, dst: int = 0, group=None):
+    """Render one frame split by tile rows: `render_band(r0, r1)` returns this rank's [3,H,W] image
+    with its band rendered.  Returns (assembled image on dst / None, bands)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    gy = (height + 15) // 16
+    bands = split_tile_rows(gy, world, weights)
+    r0, r1 = bands[rank]
+    img = render_band(r0, r1)
+    return gather_strips(img, bands, height, dst=dst, group=group), bands

@@ -71,3 +71,50 @@ def test_exp_and_threshold_edge_cases(hm):
         assert hm.hm_exp(x) == orc.exp(x)
     for op in [0.0, 1e-9, 0.0039, 0.003921569, 0.00392157, 0.01, 0.5, 0.99, 1.0, 2.0]:
         assert hm.hm_alpha_threshold(op) == orc.alpha_threshold(op)
+
+
+def test_cull_rect_is_conservative(hm):
+    """cull_rect may only drop a (Gaussian, rectangle) pair if no pixel in the rectangle passes."""
+    W, H, P = 1920, 1080, 120_000
+    sc, cfg = scenes.make_config_scene("C3", P=P)
+    cam = orc.make_camera(scenes.CAM_POS, scenes.CAM_TARGET, scenes.world_up(cfg.world), W, H)
+    fr = orc.forward(sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, orc.view_params(cam))
+    n = fr.num_rendered
+    gx = (W + 15) // 16
+    tiles = (fr.keys_sorted >> np.uint64(32)).astype(np.int64)
+    ids = fr.vals_sorted.astype(np.int64)
+    rng = np.random.default_rng(0)
+    thr_all = np.array([orc.alpha_threshold(float(o)) for o in sc.opacity[:P]], np.float32)
+    stats = {}
+    for name, (w, h) in {"tile16x16": (16, 16), "patch8x4": (8, 4)}.items():
+        tx, ty = (tiles % gx) * 16, (tiles // gx) * 16
+        ox = rng.integers(0, 16 // w, n) * w
+        oy = rng.integers(0, 16 // h, n) * h
+        rect = np.stack([tx + ox, ty + oy, tx + ox + w - 1, ty + oy + h - 1], axis=1).astype(np.int32)
+        mean = np.ascontiguousarray(fr.means_2d[ids])
+        conic = np.ascontiguousarray(fr.conic[ids])
+        thr = np.ascontiguousarray(thr_all[ids])
+        out = np.zeros(n, np.uint8)
+        hm.hm_cull_check(C.c_long(n), _p(mean), _p(conic), _p(thr), _p(rect), _p(out))
+        assert not np.any(out == 3), "cull_rect dropped a contributing pair (%s)" % name
+        dropped, empty = np.mean(out & 1), np.mean((out & 2) == 0)
+        stats[name] = (dropped, empty)
+        assert dropped > 0.8 * empty - 0.01  # and it is tight: it finds most of the empty rectangles
+    print(stats)
+    # adversarial: extremely elongated / huge / tiny Gaussians around random rectangles
+    m = 200_000
+    ang = rng.uniform(0, np.pi, m)
+    l1 = 10 ** rng.uniform(-0.5, 7, m)
+    l2 = 10 ** rng.uniform(-0.5, 1, m)
+    ca, sa = np.cos(ang), np.sin(ang)
+    cxx, cxy, cyy = ca * ca * l1 + sa * sa * l2, ca * sa * (l1 - l2), sa * sa * l1 + ca * ca * l2
+    det = cxx * cyy - cxy * cxy
+    conic = np.stack([cyy / det, -cxy / det, cxx / det], axis=1).astype(np.float32)
+    mean = rng.uniform(-3000, 5000, (m, 2)).astype(np.float32)
+    x0 = rng.integers(0, 1900, m)
+    y0 = rng.integers(0, 1060, m)
+    rect = np.stack([x0, y0, x0 + rng.integers(0, 16, m), y0 + rng.integers(0, 16, m)], axis=1).astype(np.int32)
+    thr = (-10 ** rng.uniform(-3, 0.75, m)).astype(np.float32)
+    out = np.zeros(m, np.uint8)
+    hm.hm_cull_check(C.c_long(m), _p(mean), _p(conic), _p(thr), _p(rect), _p(out))
+    assert not np.any(out == 3)
