@@ -2,25 +2,28 @@
 // Replaces m_forward_render_shader (lcgs/src/gs_tile_splatter/shader.cpp:171-288).
 //
 // One 256-thread CTA per 16x16 tile; each warp owns an 8x4 pixel patch.  The tile's depth-sorted
-// list is consumed in rounds of 256 candidates:
-//   1. every thread gathers one Gaussian's packed record (pixel mean, pre-scaled conic, alpha-test
-//      threshold, opacity, colour: 48 B) and tests it against the TILE rectangle with cull_rect();
-//      survivors are compacted, order preserved, into shared memory (ballot + prefix);
-//   2. each warp tests 32 survivors at a time, one per lane, against ITS 8x4 PATCH and walks only
-//      the set bits of the ballot, all 32 pixels evaluating the same Gaussian with broadcast LDS.
+// list is consumed in rounds of 256 candidates through a double-buffered shared-memory stage:
+//   produce (round r+1): every thread gathers one Gaussian's packed 48-byte record (pixel mean,
+//      pre-scaled conic, alpha-test threshold, opacity, colour), tests it against the TILE
+//      rectangle with cull_rect(), and each warp compacts its survivors, order preserved, into its
+//      own 32-slot segment (ballot + popc; no block-wide prefix, no extra barrier);
+//   consume (round r): each warp walks the 8 segments; per segment one lane per survivor tests it
+//      against the warp's 8x4 PATCH, and only the ballot's set bits are evaluated, all 32 pixels on
+//      the same Gaussian with broadcast LDS.128.
+// The global gathers of round r+1 are in flight while round r is blended, and there is ONE
+// __syncthreads per round (it also carries the block-wide "every pixel saturated" vote).
 // cull_rect() (lcgs_math.cuh) is conservative with respect to the per-pixel float evaluation, so
-// culling never changes a pixel: it only removes pairs the alpha test would have skipped.  On the
-// C3 scene 42 % of the (Gaussian, tile) instances the reference's loose rect bins never touch the
-// tile, and 78 % of the (Gaussian, patch) pairs are empty -- the reference evaluates all of them
-// for all 256 pixels.
-// Further differences from the reference that do not change results: colour is staged with the
-// batch instead of fetched from global memory per contributing pair (shader.cpp:268-269); the
-// alpha >= 1/255 test is a compare against a per-Gaussian power threshold, so rejected pairs cost
-// no exp; __syncthreads_and(done) stops fetching once every pixel of the tile has saturated (the
-// reference keeps loading and barrier-ing until the list ends, shader.cpp:226-277).
+// culling only removes pairs the alpha test would have skipped: on the C3 scene 42 % of the
+// (Gaussian, tile) instances binned by the reference's loose rect never touch their tile and 78 %
+// of the (Gaussian, patch) pairs are empty -- the reference evaluates all of them for 256 pixels.
+// Other differences that do not change results: colour is staged with the batch instead of fetched
+// from global memory per contributing pair (shader.cpp:268-269); the alpha >= 1/255 test is a
+// compare against a per-Gaussian power threshold, so no exp is needed to reject; the tile stops as
+// soon as every pixel has saturated (the reference keeps loading and barrier-ing until the list
+// ends, shader.cpp:226-277).
 //
-// Compute-bound (FP32 issue + shared memory), not HBM-bound; HBM side is 4 B id + 32..48 B record
-// per instance (mostly L2 hits) + 12 B per pixel.
+// Compute-bound (FP32 issue + shared memory), not HBM-bound; HBM side is 4 B id + 48 B record per
+// instance (mostly L2 hits) + 12 B per pixel.
 #include "common.cuh"
 
 namespace lcgs_b200 {
@@ -28,7 +31,26 @@ namespace lcgs_b200 {
 constexpr int kBlendThreads = 256;
 constexpr int kBlendWarps   = kBlendThreads / 32;
 
-__global__ void __launch_bounds__(kBlendThreads)
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float ex2_ftz(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(kBlendThreads, 5)
     blend_kernel(int W, int H, uint32_t gx, uint32_t row0, float bg0, float bg1, float bg2,
                  const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                  const float4* __restrict__ records, const uint32_t* __restrict__ d_num_rendered,
@@ -38,14 +60,17 @@ __global__ void __launch_bounds__(kBlendThreads)
     // untouched (lcgs/src/gs_tile_splatter/impl.cpp:109, quirk Q10)
     if (d_num_rendered && *d_num_rendered == 0u) return;
 
-    __shared__ float4   s_a[kBlendThreads];  // pix.x, pix.y, -0.5*conic.x, -conic.y
-    __shared__ float4   s_b[kBlendThreads];  // -0.5*conic.z, threshold, opacity, -
-    __shared__ float4   s_c[kBlendThreads];  // r, g, b, -
-    __shared__ uint32_t s_cnt[kBlendWarps];
+    // [buffer][plane][slot]: plane 0 = (pix.x, pix.y, -0.5*conic.x, -conic.y),
+    // plane 1 = (-0.5*conic.z, threshold, opacity, -), plane 2 = (r, g, b, -)
+    __shared__ float4   s_rec[2][3][kBlendThreads];
+    __shared__ uint32_t s_cnt[2][kBlendWarps];
 
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL    = 0xFFFFFFFFu;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t sbase   = (uint32_t)__cvta_generic_to_shared(&s_rec[0][0][0]);
+    constexpr uint32_t kPlane = kBlendThreads * 16u, kBuf = 3u * kPlane;
+
     // 8x4 pixel patch per warp: warps tile the 16x16 block as 2 columns x 4 rows of patches
     const int tile_x0 = blockIdx.x * 16, tile_y0 = (row0 + blockIdx.y) * 16;
     const int patch_x0 = tile_x0 + (warp & 1) * 8, patch_y0 = tile_y0 + (warp >> 1) * 4;
@@ -58,77 +83,94 @@ __global__ void __launch_bounds__(kBlendThreads)
 
     const uint32_t tile  = blockIdx.x + blockIdx.y * gx;
     const uint2    range = __ldg(ranges + tile);
+    const uint32_t len   = range.y > range.x ? range.y - range.x : 0u;
+    const uint32_t nrounds = (len + kBlendThreads - 1) / kBlendThreads;
 
     float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
     bool  done = !inside;
 
-    for (uint32_t start = range.x; start < range.y; start += kBlendThreads) {
-        // barrier protecting the staging buffers + block-wide early exit
-        if (__syncthreads_and(done)) break;
-
-        // ---- gather one candidate per thread, cull against the tile, compact ----------------------
-        const uint32_t idx  = start + tid;
-        bool           keep = false;
-        float4         a, b;
-        const float4*  rec = nullptr;
-        if (idx < range.y) {
-            rec  = records + (size_t)__ldg(point_list + idx) * kRecordFloat4s;
-            a    = __ldg(rec);
-            b    = __ldg(rec + 1);
-            keep = !cull_rect(a.x, a.y, a.z, a.w, b.x, b.y, tx0, ty0, tx1, ty1);
-        }
+    // cull one gathered candidate against the tile and append it to this warp's segment of `buf`
+    auto produce = [&](uint32_t buf, bool valid, const float4& a, const float4& b, const float4& c) {
+        const bool     keep = valid && !cull_rect(a.x, a.y, a.z, a.w, b.x, b.y, tx0, ty0, tx1, ty1);
         const unsigned kept = __ballot_sync(FULL, keep);
-        if (lane == 0) s_cnt[warp] = __popc(kept);
-        __syncthreads();
-        uint32_t slot = __popc(kept & lt_mask), cnt = 0;
-#pragma unroll
-        for (int w = 0; w < kBlendWarps; w++) {
-            const uint32_t c = s_cnt[w];
-            if (w < warp) slot += c;
-            cnt += c;
-        }
         if (keep) {
-            s_a[slot] = a;
-            s_b[slot] = b;
-            s_c[slot] = __ldg(rec + 2);
+            const uint32_t slot = warp * 32 + __popc(kept & lt_mask);
+            const uint32_t addr = sbase + buf * kBuf + slot * 16u;
+            sts128(addr, a);
+            sts128(addr + kPlane, b);
+            sts128(addr + 2u * kPlane, c);
         }
-        __syncthreads();
+        if (lane == 0) s_cnt[buf][warp] = __popc(kept);
+    };
 
-        // ---- per warp: cull 32 survivors at a time against the patch, evaluate the hits ------------
-        for (uint32_t base = 0; base < cnt; base += 32) {
-            if (__all_sync(FULL, done)) break;
-            const uint32_t g   = base + lane;
-            bool           hit = false;
-            if (g < cnt) {
-                const float4 ga = s_a[g];
-                const float4 gb = s_b[g];
-                hit             = !cull_rect(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, wx0, wy0, wx1, wy1);
-            }
-            unsigned hits = __ballot_sync(FULL, hit);
-            while (hits) {
-                const uint32_t j = base + (uint32_t)__ffs(hits) - 1u;
-                hits &= hits - 1u;
-                if (done) continue;
-                const float4 ea = s_a[j];
-                const float4 eb = s_b[j];
-                // canonical evaluation (shared with the oracle), two explicit fused ops
-                const float power = blend_power(ea.z, ea.w, eb.x, ea.x - pxf, ea.y - pyf);
-                if (power > 0.0f || power < eb.y) continue;  // shader.cpp:257,259
-                const float alpha  = fminf(0.99f, eb.z * __expf(power));
-                const float test_T = T * (1.0f - alpha);
-                if (test_T < 0.0001f) {  // shader.cpp:261-265: saturated, this entry is not blended
-                    done = true;
-                    continue;
+    // prologue: round 0 into buffer 0; prefetch the id of round 1
+    float4   ra, rb, rc;
+    uint32_t next_id = 0;
+    {
+        const bool valid = (uint32_t)tid < len;
+        if (valid) {
+            const float4* rec = records + (size_t)__ldg(point_list + range.x + tid) * kRecordFloat4s;
+            ra = __ldg(rec); rb = __ldg(rec + 1); rc = __ldg(rec + 2);
+        }
+        if (kBlendThreads + (uint32_t)tid < len) next_id = __ldg(point_list + range.x + kBlendThreads + tid);
+        produce(0u, valid, ra, rb, rc);
+    }
+    __syncthreads();
+
+    for (uint32_t r = 0; r < nrounds; r++) {
+        const uint32_t buf = r & 1u;
+        // ---- issue the gathers of round r+1 (consumed after the blend below) ------------------------
+        const uint32_t nidx       = (r + 1u) * kBlendThreads + tid;
+        const bool     next_valid = nidx < len;
+        if (next_valid) {
+            const float4* rec = records + (size_t)next_id * kRecordFloat4s;
+            ra = __ldg(rec); rb = __ldg(rec + 1); rc = __ldg(rec + 2);
+        }
+        if (nidx + kBlendThreads < len) next_id = __ldg(point_list + range.x + nidx + kBlendThreads);
+
+        // ---- consume round r: per segment, cull against the patch, evaluate the hits ----------------
+        if (!__all_sync(FULL, done)) {
+            const uint32_t abase = sbase + buf * kBuf;
+#pragma unroll 1
+            for (int seg = 0; seg < kBlendWarps; seg++) {
+                const uint32_t cnt = s_cnt[buf][seg];
+                bool           hit = false;
+                if ((uint32_t)lane < cnt) {
+                    const float4 ga = lds128(abase + (seg * 32 + lane) * 16u);
+                    const float4 gb = lds128(abase + kPlane + (seg * 32 + lane) * 16u);
+                    hit             = !cull_rect(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, wx0, wy0, wx1, wy1);
                 }
-                const float4 ec = s_c[j];
-                const float  w  = T * alpha;
-                C0 = __fmaf_rn(w, ec.x, C0);
-                C1 = __fmaf_rn(w, ec.y, C1);
-                C2 = __fmaf_rn(w, ec.z, C2);
-                T  = test_T;
+                unsigned hits = __ballot_sync(FULL, hit);
+                while (hits) {
+                    const uint32_t addr = abase + (seg * 32 + __ffs(hits) - 1) * 16u;
+                    hits &= hits - 1u;
+                    const float4 ea = lds128(addr);
+                    const float4 eb = lds128(addr + kPlane);
+                    const float4 ec = lds128(addr + 2u * kPlane);
+                    // canonical evaluation (shared with the oracle), two explicit fused ops
+                    const float power = blend_power(ea.z, ea.w, eb.x, ea.x - pxf, ea.y - pyf);
+                    // shader.cpp:257,259: skipped pairs (and saturated pixels) are predicated off
+                    const bool  ok     = !done && !(power > 0.0f) && !(power < eb.y);
+                    const float alpha  = fminf(0.99f, eb.z * ex2_ftz(power * 1.4426950408889634f));
+                    const float test_T = T * (1.0f - alpha);
+                    const bool  blend  = ok && !(test_T < 0.0001f);  // shader.cpp:261-265
+                    done               = done || (ok && !blend);     // saturated: this entry is not blended
+                    const float w      = blend ? T * alpha : 0.0f;
+                    C0 = __fmaf_rn(w, ec.x, C0);
+                    C1 = __fmaf_rn(w, ec.y, C1);
+                    C2 = __fmaf_rn(w, ec.z, C2);
+                    T  = blend ? test_T : T;
+                }
+                if (__all_sync(FULL, done)) break;
             }
         }
+
+        // ---- produce round r+1 into the other buffer ------------------------------------------------
+        if (r + 1u < nrounds) produce(buf ^ 1u, next_valid, ra, rb, rc);
+        // one barrier per round: publishes buffer buf^1, retires buffer buf, votes on early exit
+        if (__syncthreads_and(done)) break;
     }
+
     if (inside) {
         const size_t plane = (size_t)W * (size_t)H;
         const size_t pix   = (size_t)px + (size_t)W * (size_t)py;

@@ -400,6 +400,17 @@ LCGS_HD float blend_power(float a, float b, float c, float dx, float dy)
 #endif
 }
 
+// quotient used only to locate the maximiser along an edge; an error of a few ulp moves the
+// evaluated maximum by O(ulp^2), far inside the margin, so the device may use the fast divide
+LCGS_HD float cull_div(float x, float y)
+{
+#if defined(__CUDA_ARCH__)
+    return __fdividef(x, y);
+#else
+    return x / y;
+#endif
+}
+
 LCGS_HD bool cull_rect(float mx, float my, float a, float b, float c, float thr, float x0, float y0, float x1, float y1)
 {
     if (!(thr <= 0.0f)) return thr > 0.0f;  // +inf: nothing ever passes; NaN: keep
@@ -413,13 +424,13 @@ LCGS_HD bool cull_rect(float mx, float my, float a, float b, float c, float thr,
     float pmax = -INFINITY;
     if (!in_x) {
         const float xe = dxl > 0.0f ? dxl : dxh;  // edge facing the mean
-        float       dy = -(b * xe) / (2.0f * c);
+        float       dy = cull_div(-(b * xe), 2.0f * c);
         dy             = fminf(fmaxf(dy, dyl), dyh);
         pmax           = fmaxf(pmax, (a * xe) * xe + (b * xe) * dy + (c * dy) * dy);
     }
     if (!in_y) {
         const float ye = dyl > 0.0f ? dyl : dyh;
-        float       dx = -(b * ye) / (2.0f * a);
+        float       dx = cull_div(-(b * ye), 2.0f * a);
         dx             = fminf(fmaxf(dx, dxl), dxh);
         pmax           = fmaxf(pmax, (a * dx) * dx + (b * dx) * ye + (c * ye) * ye);
     }

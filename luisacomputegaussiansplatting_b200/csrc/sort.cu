@@ -11,6 +11,8 @@
 // exactly what the CPU oracle's stable sort yields.
 //
 // HBM-bound: algorithmic bytes = 8*n (histogram) + 24*n per pass.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lcgs_b200 {
@@ -67,8 +69,9 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// exclusive scan of one value per thread over a 256-thread block
-__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_warp /* [8] */, uint32_t* total)
+// exclusive scan of one value per thread over a THREADS-thread block
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp /* [THREADS/32] */)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t  x    = v;
@@ -79,75 +82,89 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
     }
     if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    uint32_t pre = 0, tot = 0;
+    uint32_t pre = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-        const uint32_t s = s_warp[w];
-        if (w < warp) pre += s;
-        tot += s;
-    }
+    for (int w = 0; w < THREADS / 32; w++)
+        if (w < warp) pre += s_warp[w];
     __syncthreads();  // s_warp may be reused
-    if (total) *total = tot;
     return pre + x - v;
 }
 
 // ---- one onesweep pass -------------------------------------------------------------------------
-// Shared memory (dynamic, 59.4 KB -> three CTAs per SM):
-//   s_warp_hist [8][256] u32   per-warp digit counters, then exclusive prefix over warps
-//   s_keys      [4096]   u64   tile's keys in tile-sorted order
-//   s_vals      [4096]   u32   tile's values in tile-sorted order
-//   s_tile_start[256]    u32   exclusive digit prefix inside the tile
-//   s_digit_base[256]    u32   global base of the digit minus s_tile_start
-constexpr size_t kSweepSmemBytes = (size_t)(kSortThreads / 32) * kRadix * 4 + (size_t)kSortTile * 8 + (size_t)kSortTile * 4 +
-                                   (size_t)kRadix * 4 * 2 + 64;
+// Template: THREADS x ITEMS pairs per tile (warp-striped), PREFETCH = software pipelining of the
+// next tile's key loads behind the current tile's look-back and write-out.
+// Shared memory (dynamic):
+//   s_keys      [TILE]       u64   tile's keys in tile-sorted order
+//   s_vals      [TILE]       u32   tile's values in tile-sorted order
+//   s_warp_hist [WARPS][256] u32   per-warp digit counters, then exclusive prefix over warps
+//   s_tile_start[256]        u32   exclusive digit prefix inside the tile
+//   s_digit_base[256]        u32   global base of the digit minus s_tile_start
 constexpr int kLookbackWindow = 4;
 
-__global__ void __launch_bounds__(kSortThreads, 3)
+template <int THREADS, int ITEMS>
+constexpr size_t sweep_smem_bytes()
+{
+    return (size_t)THREADS * ITEMS * 12 + (size_t)(THREADS / 32) * kRadix * 4 + (size_t)kRadix * 4 * 2 + (THREADS / 32) * 4 + 64;
+}
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool PREFETCH>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     onesweep_pass_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
                          const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
                          const uint32_t* __restrict__ d_n, size_t capacity, const uint32_t* __restrict__ hist /* [256] */,
                          uint32_t* status /* [tiles][256] */, uint32_t* ticket, int shift, uint32_t mask)
 {
-    static_assert(kSortThreads == kRadix, "one thread per digit");
+    static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit");
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE  = THREADS * ITEMS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* const s_keys       = reinterpret_cast<unsigned long long*>(smem_raw);
-    uint32_t* const           s_vals       = reinterpret_cast<uint32_t*>(s_keys + kSortTile);
-    uint32_t* const           s_warp_hist  = s_vals + kSortTile;
-    uint32_t* const           s_tile_start = s_warp_hist + (kSortThreads / 32) * kRadix;
+    uint32_t* const           s_vals       = reinterpret_cast<uint32_t*>(s_keys + TILE);
+    uint32_t* const           s_warp_hist  = s_vals + TILE;
+    uint32_t* const           s_tile_start = s_warp_hist + WARPS * kRadix;
     uint32_t* const           s_digit_base = s_tile_start + kRadix;
-    uint32_t* const           s_scan       = s_digit_base + kRadix;  // [8]
-    uint32_t* const           s_tile_slot  = s_scan + 8;
+    uint32_t* const           s_scan       = s_digit_base + kRadix;  // [WARPS]
+    uint32_t* const           s_ticket     = s_scan + WARPS;         // [2]
 
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned FULL    = 0xFFFFFFFFu;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const size_t   n       = resolve_n(n_host, d_n, capacity);
-    const uint32_t num_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+    const unsigned FULL      = 0xFFFFFFFFu;
+    const unsigned lt_mask   = (1u << lane) - 1u;
+    const size_t   n         = resolve_n(n_host, d_n, capacity);
+    const uint32_t num_tiles = (uint32_t)((n + TILE - 1) / TILE);
+    const uint32_t q0        = warp * (ITEMS * 32) + lane;  // warp-striped: item j sits at q0 + 32*j
+    const bool     is_digit  = tid < kRadix;
 
     // global exclusive scan of this pass's digit histogram (same for every tile)
-    const uint32_t bin_base = block_exclusive_scan_256(__ldg(hist + tid), s_scan, nullptr);
+    const uint32_t bin_base = block_exclusive_scan<THREADS>(is_digit ? __ldg(hist + tid) : 0u, s_scan);
 
-    for (;;) {
-        __syncthreads();  // previous iteration finished with shared memory
-        if (tid == 0) *s_tile_slot = atomicAdd(ticket, 1u);
-        for (int k = tid; k < (kSortThreads / 32) * kRadix; k += kSortThreads) s_warp_hist[k] = 0u;
-        __syncthreads();
-        const uint32_t tile = *s_tile_slot;
-        if (tile >= num_tiles) break;
-        const size_t   tile_base = (size_t)tile * kSortTile;
-        const uint32_t nvalid    = (uint32_t)((n - tile_base) < (size_t)kSortTile ? (n - tile_base) : (size_t)kSortTile);
-        const uint32_t q0        = warp * (kSortItems * 32) + lane;  // warp-striped: item j sits at q0 + 32*j
+    if (tid == 0) s_ticket[0] = atomicAdd(ticket, 1u);
+    __syncthreads();
+    uint32_t tile = s_ticket[0];
 
-        // ---- load keys ------------------------------------------------------------------------
-        unsigned long long key[kSortItems];
+    unsigned long long key[ITEMS];
+    auto load_keys = [&](uint32_t t) {
+        const size_t   base = (size_t)t * TILE;
+        const uint32_t nv   = t < num_tiles ? (uint32_t)((n - base) < (size_t)TILE ? (n - base) : (size_t)TILE) : 0u;
 #pragma unroll
-        for (int j = 0; j < kSortItems; j++) key[j] = (q0 + 32 * j < nvalid) ? __ldg(keys_in + tile_base + q0 + 32 * j) : ~0ull;
+        for (int j = 0; j < ITEMS; j++) key[j] = (q0 + 32 * j < nv) ? __ldg(keys_in + base + q0 + 32 * j) : ~0ull;
+    };
+    if (PREFETCH) load_keys(tile);
+
+    for (uint32_t it = 0; tile < num_tiles; it++) {
+        const size_t   tile_base = (size_t)tile * TILE;
+        const uint32_t nvalid    = (uint32_t)((n - tile_base) < (size_t)TILE ? (n - tile_base) : (size_t)TILE);
+        // the next ticket is taken early so that its keys can be prefetched; tickets are processed
+        // in increasing order by every CTA, which keeps the look-back free of deadlock
+        if (tid == 0) s_ticket[(it + 1) & 1] = atomicAdd(ticket, 1u);
+        for (int k = tid; k < WARPS * kRadix; k += THREADS) s_warp_hist[k] = 0u;
+        if (!PREFETCH) load_keys(tile);
+        __syncthreads();
 
         // ---- rank inside the warp with match_any ---------------------------------------------
-        uint32_t  rank[kSortItems];
+        uint32_t  rank[ITEMS];
         uint32_t* my_hist = s_warp_hist + warp * kRadix;
 #pragma unroll
-        for (int j = 0; j < kSortItems; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             const bool     valid = q0 + 32 * j < nvalid;
             const uint32_t d     = valid ? (uint32_t)((key[j] >> shift) & mask) : (uint32_t)kRadix;
             const unsigned peers = __match_any_sync(FULL, d);
@@ -160,36 +177,41 @@ __global__ void __launch_bounds__(kSortThreads, 3)
             rank[j] = pre + __popc(lower);
         }
         __syncthreads();
+        const uint32_t next_tile = s_ticket[(it + 1) & 1];
 
         // ---- per digit (thread d): prefix over warps, tile histogram, early publish ------------
-        uint32_t tile_count = 0;
+        uint32_t        tile_count = 0;
+        uint32_t* const my_status  = status + (size_t)tile * kRadix + tid;
+        if (is_digit) {
 #pragma unroll
-        for (int w = 0; w < kSortThreads / 32; w++) {
-            const uint32_t c              = s_warp_hist[w * kRadix + tid];
-            s_warp_hist[w * kRadix + tid] = tile_count;
-            tile_count += c;
+            for (int w = 0; w < WARPS; w++) {
+                const uint32_t c              = s_warp_hist[w * kRadix + tid];
+                s_warp_hist[w * kRadix + tid] = tile_count;
+                tile_count += c;
+            }
+            if (tile > 0) st_relaxed_u32(my_status, kStatusAggregate | tile_count);
         }
-        uint32_t* const my_status = status + (size_t)tile * kRadix + tid;
-        if (tile > 0) st_relaxed_u32(my_status, kStatusAggregate | tile_count);
-        const uint32_t tile_start = block_exclusive_scan_256(tile_count, s_scan, nullptr);
-        s_tile_start[tid]         = tile_start;
+        const uint32_t tile_start = block_exclusive_scan<THREADS>(tile_count, s_scan);
+        if (is_digit) s_tile_start[tid] = tile_start;
         __syncthreads();
 
-        // ---- scatter keys into shared memory in tile-sorted order; start the value loads --------
+        // ---- scatter keys into shared memory in tile-sorted order --------------------------------
 #pragma unroll
-        for (int j = 0; j < kSortItems; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             if (q0 + 32 * j < nvalid) {
                 const uint32_t d = (uint32_t)((key[j] >> shift) & mask);
                 rank[j] += s_tile_start[d] + my_hist[d];
                 s_keys[rank[j]] = key[j];
             }
         }
-        uint32_t val[kSortItems];
+        // ---- start the value loads of this tile and the key loads of the next one ----------------
+        uint32_t val[ITEMS];
 #pragma unroll
-        for (int j = 0; j < kSortItems; j++) val[j] = (q0 + 32 * j < nvalid) ? __ldg(vals_in + tile_base + q0 + 32 * j) : 0u;
+        for (int j = 0; j < ITEMS; j++) val[j] = (q0 + 32 * j < nvalid) ? __ldg(vals_in + tile_base + q0 + 32 * j) : 0u;
+        if (PREFETCH) load_keys(next_tile);
 
         // ---- decoupled look-back, kLookbackWindow predecessors in flight at a time --------------
-        {
+        if (is_digit) {
             uint32_t prefix = 0;
             if (tile > 0) {
                 int  p    = (int)tile - 1;
@@ -219,23 +241,57 @@ __global__ void __launch_bounds__(kSortThreads, 3)
 
         // ---- coalesced key write-out; scatter the values -----------------------------------------
 #pragma unroll
-        for (int j = 0; j < kSortItems; j++) {
-            const uint32_t q = tid + j * kSortThreads;
+        for (int j = 0; j < ITEMS; j++) {
+            const uint32_t q = tid + j * THREADS;
             if (q < nvalid) {
                 const unsigned long long k = s_keys[q];
                 keys_out[s_digit_base[(uint32_t)((k >> shift) & mask)] + q] = k;
             }
         }
 #pragma unroll
-        for (int j = 0; j < kSortItems; j++)
+        for (int j = 0; j < ITEMS; j++)
             if (q0 + 32 * j < nvalid) s_vals[rank[j]] = val[j];
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < kSortItems; j++) {
-            const uint32_t q = tid + j * kSortThreads;
+        for (int j = 0; j < ITEMS; j++) {
+            const uint32_t q = tid + j * THREADS;
             if (q < nvalid) vals_out[s_digit_base[(uint32_t)((s_keys[q] >> shift) & mask)] + q] = s_vals[q];
         }
+        __syncthreads();  // shared memory is reused by the next tile
+        tile = next_tile;
     }
+}
+
+typedef void (*SweepKernel)(const unsigned long long*, unsigned long long*, const uint32_t*, uint32_t*, size_t, const uint32_t*,
+                            size_t, const uint32_t*, uint32_t*, uint32_t*, int, uint32_t);
+struct SweepVariant {
+    SweepKernel kernel;
+    int         threads, tile, blocks_per_sm;
+    size_t      smem;
+    const char* name;
+};
+static const SweepVariant kSweepVariants[] = {
+    { onesweep_pass_kernel<256, 16, 3, false>, 256, 4096, 3, sweep_smem_bytes<256, 16>(), "256x16 3/SM" },
+    { onesweep_pass_kernel<256, 16, 2, true>, 256, 4096, 2, sweep_smem_bytes<256, 16>(), "256x16 2/SM prefetch" },
+    { onesweep_pass_kernel<512, 8, 2, true>, 512, 4096, 2, sweep_smem_bytes<512, 8>(), "512x8 2/SM prefetch" },
+    { onesweep_pass_kernel<512, 8, 2, false>, 512, 4096, 2, sweep_smem_bytes<512, 8>(), "512x8 2/SM" },
+    { onesweep_pass_kernel<512, 12, 1, true>, 512, 6144, 1, sweep_smem_bytes<512, 12>(), "512x12 1/SM prefetch" },
+    { onesweep_pass_kernel<256, 8, 5, false>, 256, 2048, 5, sweep_smem_bytes<256, 8>(), "256x8 5/SM" },
+    { onesweep_pass_kernel<256, 12, 3, true>, 256, 3072, 3, sweep_smem_bytes<256, 12>(), "256x12 3/SM prefetch" },
+};
+constexpr int kNumSweepVariants = (int)(sizeof(kSweepVariants) / sizeof(kSweepVariants[0]));
+constexpr int kMaxSweepTile     = 6144;
+constexpr int kMinSweepTile     = 2048;
+
+static int sweep_variant_index()
+{
+    static int idx = -1;
+    if (idx < 0) {
+        idx           = 0;  // default
+        const char* e = getenv("LCGS_SORT_VARIANT");
+        if (e && atoi(e) >= 0 && atoi(e) < kNumSweepVariants) idx = atoi(e);
+    }
+    return idx;
 }
 
 __global__ void __launch_bounds__(256)
@@ -254,7 +310,7 @@ __global__ void __launch_bounds__(256)
 // workspace layout: [hist: passes*256 u32][tickets are ctx scalars][status: passes*tiles*256 u32][tmp keys][tmp vals]
 static size_t sort_ws_layout(size_t n, size_t* off_status, size_t* off_keys, size_t* off_vals)
 {
-    const size_t tiles = (n + kSortTile - 1) / kSortTile;
+    const size_t tiles = (n + kMinSweepTile - 1) / kMinSweepTile;
     size_t       off   = 0;
     off += (size_t)kMaxSortPasses * kRadix * sizeof(uint32_t);
     off = (off + 255) & ~(size_t)255;
@@ -312,8 +368,9 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
     uint32_t* status    = (uint32_t*)(ws + off_status);
     auto*     tmp_keys  = (unsigned long long*)(ws + off_keys);
     uint32_t* tmp_vals  = (uint32_t*)(ws + off_vals);
-    const size_t tiles  = (bound + kSortTile - 1) / kSortTile;
-    uint32_t*    ticket = ctx->d_scalars + LCGS_SCALAR_SORT_TICKET;
+    const SweepVariant& var   = kSweepVariants[sweep_variant_index()];
+    const size_t        tiles = (bound + var.tile - 1) / var.tile;
+    uint32_t*           ticket = ctx->d_scalars + LCGS_SCALAR_SORT_TICKET;
 
     // zero histograms + look-back status (contiguous) and the tickets
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ws, 0, off_status + (size_t)info.num_passes * tiles * kRadix * sizeof(uint32_t), s));
@@ -325,22 +382,22 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     if (prof) cudaEventRecord(ctx->ev_sort[1], s);
 
-    static bool smem_attr_set = false;  // opt in to > 48 KB of dynamic shared memory once per process
-    if (!smem_attr_set) {
-        LCGS_CUDA_CHECK(ctx, cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)kSweepSmemBytes));
-        smem_attr_set = true;
+    static bool smem_attr_set[kNumSweepVariants] = {};  // opt in to > 48 KB of dynamic shared memory once per process
+    if (!smem_attr_set[sweep_variant_index()]) {
+        LCGS_CUDA_CHECK(ctx, cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
+        smem_attr_set[sweep_variant_index()] = true;
     }
-    const unsigned sweep_blocks = (unsigned)(tiles < (size_t)ctx->num_sms * 3 ? tiles : (size_t)ctx->num_sms * 3);
+    const size_t   max_ctas     = (size_t)ctx->num_sms * var.blocks_per_sm;
+    const unsigned sweep_blocks = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
     const unsigned long long* src_k = kin;
     const uint32_t*           src_v = vals_in;
     for (int p = 0; p < info.num_passes; p++) {
         const bool          to_out = ((info.num_passes - 1 - p) % 2) == 0;
         unsigned long long* dst_k  = to_out ? kout : tmp_keys;
         uint32_t*           dst_v  = to_out ? vals_out : tmp_vals;
-        onesweep_pass_kernel<<<sweep_blocks, kSortThreads, kSweepSmemBytes, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
-                                                                  hist + p * kRadix, status + (size_t)p * tiles * kRadix,
-                                                                  ticket + p, info.shift[p], info.mask[p]);
+        var.kernel<<<sweep_blocks, var.threads, var.smem, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
+                                                              hist + p * kRadix, status + (size_t)p * tiles * kRadix, ticket + p,
+                                                              info.shift[p], info.mask[p]);
         LCGS_CUDA_CHECK(ctx, cudaGetLastError());
         src_k = dst_k;
         src_v = dst_v;
