@@ -228,6 +228,10 @@ LCGS_B200_API int lcgs_b200_render(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc
  * list_capacity (the frame's image is then incomplete). */
 LCGS_B200_API int lcgs_b200_num_rendered(lcgs_b200_ctx* ctx, lcgs_b200_stream stream, int* num_rendered);
 
+/* Pipelined variant of the above: enqueue a copy of the last enqueued frame's num_rendered into
+ * (pinned) host memory on `stream`, without synchronising.  No capacity check. */
+LCGS_B200_API int lcgs_b200_read_num_rendered_async(lcgs_b200_ctx* ctx, uint32_t* host_count, lcgs_b200_stream stream);
+
 /* The read-back of app/main.cpp:313-315: enqueue a copy of the planar image to (pinned) host
  * memory on `stream`. */
 LCGS_B200_API int lcgs_b200_read_image(lcgs_b200_ctx* ctx, const lcgs_b200_frame* frame, float* host_img,

@@ -482,6 +482,16 @@ int lcgs_b200_num_rendered(lcgs_b200_ctx* ctx, lcgs_b200_stream stream, int* num
     return LCGS_B200_OK;
 }
 
+int lcgs_b200_read_num_rendered_async(lcgs_b200_ctx* ctx, uint32_t* host_count, lcgs_b200_stream stream)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, host_count, "read_num_rendered_async: null pointer");
+    LCGS_CUDA_CHECK(ctx, cudaMemcpyAsync(host_count, ctx->d_scalars + LCGS_SCALAR_NUM_RENDERED, sizeof(uint32_t),
+                                         cudaMemcpyDeviceToHost, as_stream(stream)));
+    return LCGS_B200_OK;
+}
+
 int lcgs_b200_read_image(lcgs_b200_ctx* ctx, const lcgs_b200_frame* fr, float* host_img, lcgs_b200_stream stream)
 {
     int rc = enter(ctx);

@@ -3,10 +3,12 @@
 // lcgs/src/gs_tile_splatter/impl.cpp:134-144), which the reference's README calls crude.
 //
 // One histogram kernel reads the keys once and counts every digit of every pass; then one
-// "onesweep" kernel per 8-bit digit reads each pair once and writes it once to its final place for
-// that pass: tiles (4096 pairs) are ranked in shared memory with warp-match (__match_any_sync)
-// histograms, the per-digit global offsets come from a chained-scan decoupled look-back across
-// tiles, and pairs are staged through shared memory so that global stores are coalesced runs.
+// "onesweep" kernel per digit reads each pair once and writes it once to its final place for that
+// pass: tiles are ranked in shared memory with warp-match (__match_any_sync) histograms, the
+// per-digit global offsets come from a decoupled look-back across tiles (a window of predecessors
+// in flight per step), and pairs are staged through shared memory so that global stores are
+// coalesced runs.  The next tile's keys are prefetched into registers behind the current tile's
+// look-back and write-out.  Digits are 9 bits wide (45 key bits = 5 passes instead of 6).
 // Stable: ties keep their input order, so equal (tile, depth) keys stay ordered by Gaussian index,
 // exactly what the CPU oracle's stable sort yields.
 //
@@ -17,9 +19,12 @@
 
 namespace lcgs_b200 {
 
+constexpr int      kMaxRadixBits    = 9;
+constexpr int      kMaxRadix        = 1 << kMaxRadixBits;
 constexpr uint32_t kStatusAggregate = 1u << 30;
 constexpr uint32_t kStatusInclusive = 2u << 30;
 constexpr uint32_t kStatusValueMask = (1u << 30) - 1u;
+constexpr int      kLookbackWindow  = 8;
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
 {
@@ -40,8 +45,19 @@ __device__ __forceinline__ size_t resolve_n(size_t n_host, const uint32_t* d_n, 
     return n > capacity ? capacity : n;
 }
 
+// digit of a 64-bit key: bits [shift, shift+width) -- one funnel shift + one AND
+__device__ __forceinline__ uint32_t key_digit(unsigned long long key, int shift, uint32_t mask)
+{
+    return __funnelshift_r((uint32_t)key, (uint32_t)(key >> 32), shift) & mask;  // shift < 32
+}
+__device__ __forceinline__ uint32_t key_digit_hi(unsigned long long key, int shift, uint32_t mask)
+{
+    return ((uint32_t)(key >> 32) >> (shift - 32)) & mask;  // shift >= 32
+}
+
 struct SortPassInfo {
     int      num_passes;
+    int      radix_bits;
     int      shift[kMaxSortPasses];
     uint32_t mask[kMaxSortPasses];
 };
@@ -51,8 +67,9 @@ __global__ void __launch_bounds__(256)
     radix_histogram_kernel(const unsigned long long* __restrict__ keys, size_t n_host, const uint32_t* __restrict__ d_n,
                            size_t capacity, uint32_t* __restrict__ hist, const __grid_constant__ SortPassInfo info)
 {
-    __shared__ uint32_t s_hist[kMaxSortPasses * kRadix];
-    for (int k = threadIdx.x; k < info.num_passes * kRadix; k += blockDim.x) s_hist[k] = 0u;
+    __shared__ uint32_t s_hist[kMaxSortPasses * kMaxRadix];
+    const int radix = 1 << info.radix_bits;
+    for (int k = threadIdx.x; k < info.num_passes * radix; k += blockDim.x) s_hist[k] = 0u;
     __syncthreads();
     const size_t n      = resolve_n(n_host, d_n, capacity);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -60,10 +77,11 @@ __global__ void __launch_bounds__(256)
         const unsigned long long key = __ldg(keys + k);
 #pragma unroll
         for (int p = 0; p < kMaxSortPasses; p++)
-            if (p < info.num_passes) atomicAdd(&s_hist[p * kRadix + (uint32_t)((key >> info.shift[p]) & info.mask[p])], 1u);
+            if (p < info.num_passes)
+                atomicAdd(&s_hist[(p << info.radix_bits) + (uint32_t)((key >> info.shift[p]) & info.mask[p])], 1u);
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < info.num_passes * kRadix; k += blockDim.x) {
+    for (int k = threadIdx.x; k < info.num_passes * radix; k += blockDim.x) {
         const uint32_t c = s_hist[k];
         if (c) atomicAdd(hist + k, c);
     }
@@ -91,207 +109,240 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 }
 
 // ---- one onesweep pass -------------------------------------------------------------------------
-// Template: THREADS x ITEMS pairs per tile (warp-striped), PREFETCH = software pipelining of the
-// next tile's key loads behind the current tile's look-back and write-out.
-// Shared memory (dynamic):
-//   s_keys      [TILE]       u64   tile's keys in tile-sorted order
-//   s_vals      [TILE]       u32   tile's values in tile-sorted order
-//   s_warp_hist [WARPS][256] u32   per-warp digit counters, then exclusive prefix over warps
-//   s_tile_start[256]        u32   exclusive digit prefix inside the tile
-//   s_digit_base[256]        u32   global base of the digit minus s_tile_start
-constexpr int kLookbackWindow = 4;
-
-template <int THREADS, int ITEMS>
+// THREADS x ITEMS pairs per tile (warp-striped), 2^RBITS digits (one digit per thread, THREADS >=
+// 2^RBITS).  Dynamic shared memory:
+//   s_keys [TILE]         u64  tile's keys in tile-sorted order
+//   s_vals [TILE]         u32  tile's values in tile-sorted order
+//   s_wh   [WARPS][RADIX] u32  per-warp digit counters, then each warp's first slot per digit
+//   s_base [RADIX]        u32  global position of the digit's first pair minus its first tile slot
+template <int THREADS, int ITEMS, int RBITS>
 constexpr size_t sweep_smem_bytes()
 {
-    return (size_t)THREADS * ITEMS * 12 + (size_t)(THREADS / 32) * kRadix * 4 + (size_t)kRadix * 4 * 2 + (THREADS / 32) * 4 + 64;
+    return (size_t)THREADS * ITEMS * 12 + (size_t)(THREADS / 32) * (1 << RBITS) * 4 + (size_t)(1 << RBITS) * 4 + (THREADS / 32) * 4 +
+           64;
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, bool PREFETCH>
+template <int THREADS, int ITEMS, int RBITS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     onesweep_pass_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
                          const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
-                         const uint32_t* __restrict__ d_n, size_t capacity, const uint32_t* __restrict__ hist /* [256] */,
-                         uint32_t* status /* [tiles][256] */, uint32_t* ticket, int shift, uint32_t mask)
+                         const uint32_t* __restrict__ d_n, size_t capacity, const uint32_t* __restrict__ hist /* [RADIX] */,
+                         uint32_t* status /* [tiles][RADIX] */, uint32_t* ticket, int shift, uint32_t mask,
+                         unsigned long long* dbg /* optional phase timers, LCGS_SORT_DEBUG=1 */)
 {
-    static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit");
+    constexpr int RADIX = 1 << RBITS;
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE  = THREADS * ITEMS;
+    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit");
+    static_assert((WARPS * RADIX) % THREADS == 0, "counter zeroing");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* const s_keys       = reinterpret_cast<unsigned long long*>(smem_raw);
-    uint32_t* const           s_vals       = reinterpret_cast<uint32_t*>(s_keys + TILE);
-    uint32_t* const           s_warp_hist  = s_vals + TILE;
-    uint32_t* const           s_tile_start = s_warp_hist + WARPS * kRadix;
-    uint32_t* const           s_digit_base = s_tile_start + kRadix;
-    uint32_t* const           s_scan       = s_digit_base + kRadix;  // [WARPS]
-    uint32_t* const           s_ticket     = s_scan + WARPS;         // [2]
+    unsigned long long* const s_keys   = reinterpret_cast<unsigned long long*>(smem_raw);
+    uint32_t* const           s_vals   = reinterpret_cast<uint32_t*>(s_keys + TILE);
+    uint32_t* const           s_wh     = s_vals + TILE;
+    uint32_t* const           s_base   = s_wh + WARPS * RADIX;
+    uint32_t* const           s_scan   = s_base + RADIX;  // [WARPS]
+    uint32_t* const           s_ticket = s_scan + WARPS;  // [2]
 
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned FULL      = 0xFFFFFFFFu;
+    const unsigned FULLM     = 0xFFFFFFFFu;
     const unsigned lt_mask   = (1u << lane) - 1u;
     const size_t   n         = resolve_n(n_host, d_n, capacity);
     const uint32_t num_tiles = (uint32_t)((n + TILE - 1) / TILE);
     const uint32_t q0        = warp * (ITEMS * 32) + lane;  // warp-striped: item j sits at q0 + 32*j
-    const bool     is_digit  = tid < kRadix;
+    const bool     is_digit  = tid < RADIX;
+    const bool     hi_word   = shift >= 32;  // uniform: the digit lives entirely in the key's high word
+    uint32_t* const my_hist  = s_wh + warp * RADIX;
+
+    auto digit_of = [&](unsigned long long k) -> uint32_t {
+        return hi_word ? key_digit_hi(k, shift, mask) : key_digit(k, shift, mask);
+    };
+    auto tile_valid = [&](uint32_t t) -> uint32_t {
+        const size_t base = (size_t)t * TILE;
+        return (uint32_t)((n - base) < (size_t)TILE ? (n - base) : (size_t)TILE);
+    };
 
     // global exclusive scan of this pass's digit histogram (same for every tile)
     const uint32_t bin_base = block_exclusive_scan<THREADS>(is_digit ? __ldg(hist + tid) : 0u, s_scan);
 
+    // Tiles are handed out by a ticket counter.  Every CTA takes its next ticket at the same point of
+    // its loop (the top), one tile ahead, so that the keys can be prefetched: tickets then start in
+    // (nearly) ticket order, which keeps look-back waits short, and every CTA processes its tickets in
+    // increasing order, which keeps the look-back free of deadlock.
     if (tid == 0) s_ticket[0] = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int k = 0; k < (WARPS * RADIX) / THREADS; k++) s_wh[tid + k * THREADS] = 0u;
     __syncthreads();
     uint32_t tile = s_ticket[0];
 
     unsigned long long key[ITEMS];
     auto load_keys = [&](uint32_t t) {
-        const size_t   base = (size_t)t * TILE;
-        const uint32_t nv   = t < num_tiles ? (uint32_t)((n - base) < (size_t)TILE ? (n - base) : (size_t)TILE) : 0u;
+        if (t >= num_tiles) return;
+        const unsigned long long* src = keys_in + (size_t)t * TILE + q0;
+        const uint32_t            nv  = tile_valid(t);
+        if (nv == (uint32_t)TILE) {
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) key[j] = (q0 + 32 * j < nv) ? __ldg(keys_in + base + q0 + 32 * j) : ~0ull;
+            for (int j = 0; j < ITEMS; j++) key[j] = __ldg(src + 32 * j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) key[j] = (q0 + 32 * j < nv) ? __ldg(src + 32 * j) : ~0ull;
+        }
     };
-    if (PREFETCH) load_keys(tile);
+    load_keys(tile);
 
-    for (uint32_t it = 0; tile < num_tiles; it++) {
-        const size_t   tile_base = (size_t)tile * TILE;
-        const uint32_t nvalid    = (uint32_t)((n - tile_base) < (size_t)TILE ? (n - tile_base) : (size_t)TILE);
-        // the next ticket is taken early so that its keys can be prefetched; tickets are processed
-        // in increasing order by every CTA, which keeps the look-back free of deadlock
-        if (tid == 0) s_ticket[(it + 1) & 1] = atomicAdd(ticket, 1u);
-        for (int k = tid; k < WARPS * kRadix; k += THREADS) s_warp_hist[k] = 0u;
-        if (!PREFETCH) load_keys(tile);
-        __syncthreads();
+    long long t_prev = dbg ? clock64() : 0;
+    auto      lap    = [&](int phase) {
+        if (dbg && tid == 0) {
+            const long long t = clock64();
+            atomicAdd(dbg + phase, (unsigned long long)(t - t_prev));
+            t_prev = t;
+        }
+    };
+    while (tile < num_tiles) {
+        const uint32_t nvalid = tile_valid(tile);
+        const bool     full   = nvalid == (uint32_t)TILE;
+        if (tid == 0) s_ticket[1] = atomicAdd(ticket, 1u);  // published by the barrier after ranking
 
-        // ---- rank inside the warp with match_any ---------------------------------------------
-        uint32_t  rank[ITEMS];
-        uint32_t* my_hist = s_warp_hist + warp * kRadix;
+        // ---- rank inside the warp with match_any (s_wh is zero on entry) -------------------------
+        uint32_t rank[ITEMS];
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) {
-            const bool     valid = q0 + 32 * j < nvalid;
-            const uint32_t d     = valid ? (uint32_t)((key[j] >> shift) & mask) : (uint32_t)kRadix;
-            const unsigned peers = __match_any_sync(FULL, d);
-            const unsigned lower = peers & lt_mask;
-            uint32_t       pre   = 0;
-            if (valid) pre = my_hist[d];
-            __syncwarp();
-            if (valid && lower == 0u) my_hist[d] = pre + __popc(peers);
-            __syncwarp();
-            rank[j] = pre + __popc(lower);
+            for (int j = 0; j < ITEMS; j++) {
+                const uint32_t d     = digit_of(key[j]);
+                const unsigned peers = __match_any_sync(FULLM, d);
+                const unsigned lower = peers & lt_mask;
+                const uint32_t pre   = my_hist[d];
+                __syncwarp();
+                if (lower == 0u) my_hist[d] = pre + __popc(peers);
+                __syncwarp();
+                rank[j] = pre + __popc(lower);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                const bool     valid = q0 + 32 * j < nvalid;
+                const uint32_t d     = valid ? digit_of(key[j]) : (uint32_t)RADIX;
+                const unsigned peers = __match_any_sync(FULLM, d);
+                const unsigned lower = peers & lt_mask;
+                uint32_t       pre   = 0;
+                if (valid) pre = my_hist[d];
+                __syncwarp();
+                if (valid && lower == 0u) my_hist[d] = pre + __popc(peers);
+                __syncwarp();
+                rank[j] = pre + __popc(lower);
+            }
         }
         __syncthreads();
-        const uint32_t next_tile = s_ticket[(it + 1) & 1];
+        lap(0);  // wait for keys + rank
+        const uint32_t next_tile = s_ticket[1];
 
-        // ---- per digit (thread d): prefix over warps, tile histogram, early publish ------------
+        // ---- per digit (thread d): tile histogram, early publish, first look-back window ---------
         uint32_t        tile_count = 0;
-        uint32_t* const my_status  = status + (size_t)tile * kRadix + tid;
+        uint32_t        cnt[WARPS];
+        uint32_t        st[kLookbackWindow];
+        uint32_t* const my_status = status + (size_t)tile * RADIX + tid;
+        int             p         = (int)tile - 1;
         if (is_digit) {
 #pragma unroll
             for (int w = 0; w < WARPS; w++) {
-                const uint32_t c              = s_warp_hist[w * kRadix + tid];
-                s_warp_hist[w * kRadix + tid] = tile_count;
-                tile_count += c;
+                cnt[w] = s_wh[w * RADIX + tid];
+                tile_count += cnt[w];
             }
             if (tile > 0) st_relaxed_u32(my_status, kStatusAggregate | tile_count);
+            // the predecessors' status words are requested now and consumed after the key scatter
+#pragma unroll
+            for (int k = 0; k < kLookbackWindow; k++)
+                st[k] = (p - k >= 0) ? ld_relaxed_u32(status + (size_t)(p - k) * RADIX + tid) : kStatusInclusive;
         }
         const uint32_t tile_start = block_exclusive_scan<THREADS>(tile_count, s_scan);
-        if (is_digit) s_tile_start[tid] = tile_start;
+        if (is_digit) {
+            uint32_t run = tile_start;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) {
+                s_wh[w * RADIX + tid] = run;
+                run += cnt[w];
+            }
+        }
         __syncthreads();
+        lap(1);  // digit prefix + block scan
 
         // ---- scatter keys into shared memory in tile-sorted order --------------------------------
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
-            if (q0 + 32 * j < nvalid) {
-                const uint32_t d = (uint32_t)((key[j] >> shift) & mask);
-                rank[j] += s_tile_start[d] + my_hist[d];
+            if (full || q0 + 32 * j < nvalid) {
+                rank[j] += my_hist[digit_of(key[j])];
                 s_keys[rank[j]] = key[j];
             }
         }
-        // ---- start the value loads of this tile and the key loads of the next one ----------------
-        uint32_t val[ITEMS];
-#pragma unroll
-        for (int j = 0; j < ITEMS; j++) val[j] = (q0 + 32 * j < nvalid) ? __ldg(vals_in + tile_base + q0 + 32 * j) : 0u;
-        if (PREFETCH) load_keys(next_tile);
+        lap(2);  // scatter keys
 
-        // ---- decoupled look-back, kLookbackWindow predecessors in flight at a time --------------
+        // ---- decoupled look-back: consume the window requested above, then further windows ---------
         if (is_digit) {
             uint32_t prefix = 0;
-            if (tile > 0) {
-                int  p    = (int)tile - 1;
-                bool more = true;
-                while (more) {
-                    uint32_t st[kLookbackWindow];
+            bool     more   = tile > 0;
+            while (more) {
+                if (dbg && tid == 0) atomicAdd(dbg + 8, 1ull);
+#pragma unroll
+                for (int k = 0; k < kLookbackWindow; k++) {
+                    if (!more) break;
+                    if ((st[k] >> 30) == 0u) {  // not published yet: poll again from this tile
+                        if (dbg && tid == 0) atomicAdd(dbg + 9, 1ull);
+                        p -= k;
+                        break;
+                    }
+                    prefix += st[k] & kStatusValueMask;
+                    if ((st[k] >> 30) == 2u) more = false;
+                    else if (k == kLookbackWindow - 1) p -= kLookbackWindow;
+                }
+                if (more) {
 #pragma unroll
                     for (int k = 0; k < kLookbackWindow; k++)
-                        st[k] = (p - k >= 0) ? ld_relaxed_u32(status + (size_t)(p - k) * kRadix + tid) : kStatusInclusive;
-#pragma unroll
-                    for (int k = 0; k < kLookbackWindow; k++) {
-                        if (!more) break;
-                        if ((st[k] >> 30) == 0u) {  // not published yet: poll again from this tile
-                            p -= k;
-                            break;
-                        }
-                        prefix += st[k] & kStatusValueMask;
-                        if ((st[k] >> 30) == 2u) more = false;
-                        else if (k == kLookbackWindow - 1) p -= kLookbackWindow;
-                    }
+                        st[k] = (p - k >= 0) ? ld_relaxed_u32(status + (size_t)(p - k) * RADIX + tid) : kStatusInclusive;
                 }
             }
             st_relaxed_u32(my_status, kStatusInclusive | ((prefix + tile_count) & kStatusValueMask));
-            s_digit_base[tid] = bin_base + prefix - tile_start;
+            s_base[tid] = bin_base + prefix - tile_start;
         }
-        __syncthreads();
+        lap(3);  // thread 0's own look-back
 
-        // ---- coalesced key write-out; scatter the values -----------------------------------------
+        // ---- start the value loads of this tile and the key loads of the next one ----------------
+        uint32_t        val[ITEMS];
+        const uint32_t* vsrc = vals_in + (size_t)tile * TILE + q0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) val[j] = (full || q0 + 32 * j < nvalid) ? __ldg(vsrc + 32 * j) : 0u;
+        load_keys(next_tile);
+        __syncthreads();
+        lap(4);  // issue loads + wait for the slowest digit's look-back
+
+        // ---- coalesced key write-out (remember each slot's destination), scatter the values --------
+        uint32_t dst[ITEMS];
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             const uint32_t q = tid + j * THREADS;
-            if (q < nvalid) {
+            if (full || q < nvalid) {
                 const unsigned long long k = s_keys[q];
-                keys_out[s_digit_base[(uint32_t)((k >> shift) & mask)] + q] = k;
+                dst[j]                     = s_base[digit_of(k)] + q;
+                keys_out[dst[j]]           = k;
             }
         }
 #pragma unroll
         for (int j = 0; j < ITEMS; j++)
-            if (q0 + 32 * j < nvalid) s_vals[rank[j]] = val[j];
+            if (full || q0 + 32 * j < nvalid) s_vals[rank[j]] = val[j];
+        // the per-warp counters are free again: clear them for the next tile
+#pragma unroll
+        for (int k = 0; k < (WARPS * RADIX) / THREADS; k++) s_wh[tid + k * THREADS] = 0u;
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             const uint32_t q = tid + j * THREADS;
-            if (q < nvalid) vals_out[s_digit_base[(uint32_t)((s_keys[q] >> shift) & mask)] + q] = s_vals[q];
+            if (full || q < nvalid) vals_out[dst[j]] = s_vals[q];
         }
-        __syncthreads();  // shared memory is reused by the next tile
+        lap(5);  // write-out
+        if (dbg && tid == 0) atomicAdd(dbg + 10, 1ull);
         tile = next_tile;
+        // s_ticket[1] is rewritten at the next loop top, after every thread has read it (three barriers
+        // ago); s_keys / s_vals are rewritten after two more barriers, by which time every thread has
+        // finished the loops above
     }
-}
-
-typedef void (*SweepKernel)(const unsigned long long*, unsigned long long*, const uint32_t*, uint32_t*, size_t, const uint32_t*,
-                            size_t, const uint32_t*, uint32_t*, uint32_t*, int, uint32_t);
-struct SweepVariant {
-    SweepKernel kernel;
-    int         threads, tile, blocks_per_sm;
-    size_t      smem;
-    const char* name;
-};
-static const SweepVariant kSweepVariants[] = {
-    { onesweep_pass_kernel<256, 16, 3, false>, 256, 4096, 3, sweep_smem_bytes<256, 16>(), "256x16 3/SM" },
-    { onesweep_pass_kernel<256, 16, 2, true>, 256, 4096, 2, sweep_smem_bytes<256, 16>(), "256x16 2/SM prefetch" },
-    { onesweep_pass_kernel<512, 8, 2, true>, 512, 4096, 2, sweep_smem_bytes<512, 8>(), "512x8 2/SM prefetch" },
-    { onesweep_pass_kernel<512, 8, 2, false>, 512, 4096, 2, sweep_smem_bytes<512, 8>(), "512x8 2/SM" },
-    { onesweep_pass_kernel<512, 12, 1, true>, 512, 6144, 1, sweep_smem_bytes<512, 12>(), "512x12 1/SM prefetch" },
-    { onesweep_pass_kernel<256, 8, 5, false>, 256, 2048, 5, sweep_smem_bytes<256, 8>(), "256x8 5/SM" },
-    { onesweep_pass_kernel<256, 12, 3, true>, 256, 3072, 3, sweep_smem_bytes<256, 12>(), "256x12 3/SM prefetch" },
-};
-constexpr int kNumSweepVariants = (int)(sizeof(kSweepVariants) / sizeof(kSweepVariants[0]));
-constexpr int kMaxSweepTile     = 6144;
-constexpr int kMinSweepTile     = 2048;
-
-static int sweep_variant_index()
-{
-    static int idx = -1;
-    if (idx < 0) {
-        idx           = 0;  // default
-        const char* e = getenv("LCGS_SORT_VARIANT");
-        if (e && atoi(e) >= 0 && atoi(e) < kNumSweepVariants) idx = atoi(e);
-    }
-    return idx;
 }
 
 __global__ void __launch_bounds__(256)
@@ -307,15 +358,49 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// workspace layout: [hist: passes*256 u32][tickets are ctx scalars][status: passes*tiles*256 u32][tmp keys][tmp vals]
+typedef void (*SweepKernel)(const unsigned long long*, unsigned long long*, const uint32_t*, uint32_t*, size_t, const uint32_t*,
+                            size_t, const uint32_t*, uint32_t*, uint32_t*, int, uint32_t, unsigned long long*);
+struct SweepVariant {
+    SweepKernel kernel;
+    int         threads, tile, radix_bits, blocks_per_sm;
+    size_t      smem;
+    const char* name;
+};
+#define LCGS_SWEEP(T, I, R, B) \
+    { onesweep_pass_kernel<T, I, R, B>, T, T * I, R, B, sweep_smem_bytes<T, I, R>(), #T "x" #I " r" #R " " #B "/SM" }
+static const SweepVariant kSweepVariants[] = {
+    LCGS_SWEEP(512, 8, 9, 2),  // default: 9-bit digits, 2 CTAs x 16 warps per SM
+    LCGS_SWEEP(512, 8, 8, 2),
+    LCGS_SWEEP(256, 16, 8, 2),
+    LCGS_SWEEP(256, 16, 8, 3),
+    LCGS_SWEEP(512, 12, 9, 1),
+    LCGS_SWEEP(1024, 4, 9, 1),
+    LCGS_SWEEP(512, 6, 9, 2),
+    LCGS_SWEEP(256, 8, 8, 4),
+};
+constexpr int kNumSweepVariants = (int)(sizeof(kSweepVariants) / sizeof(kSweepVariants[0]));
+constexpr int kMinSweepTile     = 2048;
+
+static int sweep_variant_index()
+{
+    static int idx = -1;
+    if (idx < 0) {
+        idx           = 0;
+        const char* e = getenv("LCGS_SORT_VARIANT");
+        if (e && atoi(e) >= 0 && atoi(e) < kNumSweepVariants) idx = atoi(e);
+    }
+    return idx;
+}
+
+// workspace layout: [hist: passes*512 u32][status: passes*tiles*RADIX u32][tmp keys][tmp vals]
 static size_t sort_ws_layout(size_t n, size_t* off_status, size_t* off_keys, size_t* off_vals)
 {
     const size_t tiles = (n + kMinSweepTile - 1) / kMinSweepTile;
     size_t       off   = 0;
-    off += (size_t)kMaxSortPasses * kRadix * sizeof(uint32_t);
+    off += (size_t)kMaxSortPasses * kMaxRadix * sizeof(uint32_t);
     off = (off + 255) & ~(size_t)255;
     if (off_status) *off_status = off;
-    off += (size_t)kMaxSortPasses * tiles * kRadix * sizeof(uint32_t);
+    off += (size_t)kMaxSortPasses * tiles * kMaxRadix * sizeof(uint32_t);
     off = (off + 255) & ~(size_t)255;
     if (off_keys) *off_keys = off;
     off += n * sizeof(uint64_t);
@@ -338,14 +423,18 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
     LCGS_REQUIRE(ctx, bound <= (size_t)kStatusValueMask, "sort: more than 2^30-1 pairs");
     if (!d_n) capacity = n_host;
 
-    SortPassInfo info;
-    const int    bits = end_bit - begin_bit;
-    info.num_passes   = (bits + kRadixBits - 1) / kRadixBits;
+    const SweepVariant& var   = kSweepVariants[sweep_variant_index()];
+    const int           bits  = end_bit - begin_bit;
+    const int           rbits = var.radix_bits;
+    SortPassInfo        info;
+    info.radix_bits = rbits;
+    info.num_passes = (bits + rbits - 1) / rbits;
+    LCGS_REQUIRE(ctx, info.num_passes <= kMaxSortPasses, "sort: too many passes");
     for (int p = 0; p < kMaxSortPasses; p++) {
-        const int lo   = begin_bit + p * kRadixBits;
-        const int w    = (p < info.num_passes) ? ((end_bit - lo) < kRadixBits ? (end_bit - lo) : kRadixBits) : 0;
-        info.shift[p]  = lo < 64 ? lo : 0;
-        info.mask[p]   = w > 0 ? ((1u << w) - 1u) : 0u;
+        const int lo  = begin_bit + p * rbits;
+        const int w   = (p < info.num_passes) ? ((end_bit - lo) < rbits ? (end_bit - lo) : rbits) : 0;
+        info.shift[p] = lo < 64 ? lo : 0;
+        info.mask[p]  = w > 0 ? ((1u << w) - 1u) : 0u;
     }
 
     const auto* kin  = reinterpret_cast<const unsigned long long*>(keys_in);
@@ -363,17 +452,17 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
     const size_t bytes = sort_ws_layout(bound, &off_status, &off_keys, &off_vals);
     int          rc    = ws_reserve(ctx, ctx->sort_ws, bytes);
     if (rc) return rc;
-    char*     ws        = (char*)ctx->sort_ws.ptr;
-    uint32_t* hist      = (uint32_t*)ws;
-    uint32_t* status    = (uint32_t*)(ws + off_status);
-    auto*     tmp_keys  = (unsigned long long*)(ws + off_keys);
-    uint32_t* tmp_vals  = (uint32_t*)(ws + off_vals);
-    const SweepVariant& var   = kSweepVariants[sweep_variant_index()];
-    const size_t        tiles = (bound + var.tile - 1) / var.tile;
-    uint32_t*           ticket = ctx->d_scalars + LCGS_SCALAR_SORT_TICKET;
+    char*        ws       = (char*)ctx->sort_ws.ptr;
+    uint32_t*    hist     = (uint32_t*)ws;
+    uint32_t*    status   = (uint32_t*)(ws + off_status);
+    auto*        tmp_keys = (unsigned long long*)(ws + off_keys);
+    uint32_t*    tmp_vals = (uint32_t*)(ws + off_vals);
+    const int    radix    = 1 << rbits;
+    const size_t tiles    = (bound + var.tile - 1) / var.tile;
+    uint32_t*    ticket   = ctx->d_scalars + LCGS_SCALAR_SORT_TICKET;
 
     // zero histograms + look-back status (contiguous) and the tickets
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ws, 0, off_status + (size_t)info.num_passes * tiles * kRadix * sizeof(uint32_t), s));
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ws, 0, off_status + (size_t)info.num_passes * tiles * radix * sizeof(uint32_t), s));
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, kMaxSortPasses * sizeof(uint32_t), s));
 
     const bool prof = ctx->profiling && ctx->ev_sort[0];
@@ -389,6 +478,26 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
     }
     const size_t   max_ctas     = (size_t)ctx->num_sms * var.blocks_per_sm;
     const unsigned sweep_blocks = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
+    // LCGS_SORT_DEBUG=1: accumulate per-phase clock64() deltas of thread 0 of every CTA (tuning only)
+    static unsigned long long* dbg      = nullptr;
+    static int                 dbg_init = 0;
+    if (!dbg_init) {
+        dbg_init = 1;
+        if (getenv("LCGS_SORT_DEBUG")) {
+            LCGS_CUDA_CHECK(ctx, cudaMalloc(&dbg, 16 * sizeof(unsigned long long)));
+            LCGS_CUDA_CHECK(ctx, cudaMemset(dbg, 0, 16 * sizeof(unsigned long long)));
+        }
+    }
+    if (dbg && getenv("LCGS_SORT_DEBUG_PRINT")) {
+        unsigned long long h[16];
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaMemset(dbg, 0, sizeof(h));
+        if (h[10])
+            fprintf(stderr, "[sort dbg] tiles %llu cycles/tile: rank %llu prefix %llu scatter %llu lookback(t0) %llu lb-wait %llu write %llu | "
+                            "lookback steps/tile %.2f spins/tile %.2f\n",
+                    h[10], h[0] / h[10], h[1] / h[10], h[2] / h[10], h[3] / h[10], h[4] / h[10], h[5] / h[10],
+                    (double)h[8] / h[10], (double)h[9] / h[10]);
+    }
     const unsigned long long* src_k = kin;
     const uint32_t*           src_v = vals_in;
     for (int p = 0; p < info.num_passes; p++) {
@@ -396,8 +505,8 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
         unsigned long long* dst_k  = to_out ? kout : tmp_keys;
         uint32_t*           dst_v  = to_out ? vals_out : tmp_vals;
         var.kernel<<<sweep_blocks, var.threads, var.smem, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
-                                                              hist + p * kRadix, status + (size_t)p * tiles * kRadix, ticket + p,
-                                                              info.shift[p], info.mask[p]);
+                                                              hist + (size_t)p * radix, status + (size_t)p * tiles * radix,
+                                                              ticket + p, info.shift[p], info.mask[p], dbg);
         LCGS_CUDA_CHECK(ctx, cudaGetLastError());
         src_k = dst_k;
         src_v = dst_v;

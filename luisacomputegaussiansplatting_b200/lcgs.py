@@ -420,6 +420,17 @@ class Renderer:
         d = self.device
         d.check(d.lib.lcgs_b200_read_image(d.ctx, C.byref(self.c_frame), host_img.data_ptr(), _stream_handle(stream)))
 
+    def set_target(self, img: torch.Tensor):
+        """Render the following frames into another planar [3*H*W] float32 device buffer."""
+        assert img.numel() == 3 * self.W * self.H and img.dtype == torch.float32
+        self.img = img
+        self.c_frame.target_img = _ptr(img)
+
+    def read_num_rendered_async(self, host_count: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
+        """Enqueue a copy of the last enqueued frame's num_rendered into a pinned int32 host tensor."""
+        d = self.device
+        d.check(d.lib.lcgs_b200_read_num_rendered_async(d.ctx, host_count.data_ptr(), _stream_handle(stream)))
+
     def image(self) -> torch.Tensor:
         return self.img.view(3, self.H, self.W)
 
