@@ -198,7 +198,9 @@ class ClockSampler:
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 
-KERNELS_PER_FRAME = 12  # preprocess, scan, duplicate_keys, histogram, 6 onesweep passes, ranges, blend
+# preprocess, scan+compact, [depth sort: histogram + 4 passes], gather scan, duplicate_keys, [tile sort: histogram + 2 passes],
+# ranges, blend
+KERNELS_PER_FRAME = 14
 
 
 def run_b200(args):
@@ -362,9 +364,13 @@ def run_b200(args):
     passes = sort_acc["num_passes"]
     pass_ms = sort_acc["passes_ms"] / passes
     achieved = 24.0 * N / (pass_ms * 1e-3) / 1e9
-    # algorithmic bytes per stage
-    alg = {"preprocess": 48.0 * P + 228.0 * V, "scan": 8.0 * P, "duplicate_keys": 4.0 * P + 16.0 * V + 12.0 * N,
-           "sort": N * (8.0 + 24.0 * passes), "ranges": 8.0 * N + 16.0 * T, "blend": 40.0 * N + 12.0 * W * H}
+    # algorithmic bytes per stage of the data flow that actually runs (M = Gaussians touching a tile): the Gaussians
+    # are depth-sorted first (8-byte pairs), so the 12-byte instance pairs need `passes` tile-bit passes only.
+    # The reference's data flow would move N*(8+24*ceil((32+log2 T)/8)) bytes in the sort alone.
+    M = touching
+    alg = {"preprocess": 48.0 * P + 228.0 * V, "scan": 8.0 * P + 12.0 * M, "depth_sort": M * (4.0 + 16.0 * 4) + 16.0 * M,
+           "duplicate_keys": 20.0 * M + 12.0 * N, "sort": N * (8.0 + 24.0 * passes), "ranges": 8.0 * N + 16.0 * T,
+           "blend": 40.0 * N + 12.0 * W * H}
     stages = {k: {"ms": round(v, 4), "alg_GB": round(alg[k] / 1e9, 4), "GBps": round(alg[k] / (v * 1e-3) / 1e9, 1),
                   "frac_of_hbm_peak": round(alg[k] / (v * 1e-3) / 1e9 / peak, 3)} for k, v in stage_acc.items()}
     stages["blend"]["bound"] = "fp32+shared-memory (not HBM)"

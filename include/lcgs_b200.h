@@ -219,7 +219,10 @@ LCGS_B200_API int lcgs_b200_splat_forward(lcgs_b200_ctx* ctx, int num_gaussians,
  * + GSTileSplatter::forward with the three per-Gaussian passes fused into one kernel.  Enqueue
  * only, no allocation after lcgs_b200_ctx_reserve: capturable in a CUDA graph.  In this fused path
  * color is written only for Gaussians with tiles_touched > 0 (no other output depends on the
- * rest), and NULL optional buffers are skipped. */
+ * rest), NULL optional buffers are skipped, and the unsorted lists are emitted in depth order
+ * (the Gaussians are sorted by depth first so that the instances only need a stable sort by tile):
+ * point_list_keys_unsorted / point_list_unsorted hold the same pairs as the reference's in a
+ * different order, while point_list_keys, point_list and ranges are bit-identical. */
 LCGS_B200_API int lcgs_b200_render(lcgs_b200_ctx* ctx, const lcgs_b200_scene* scene, const lcgs_b200_view_params* vp,
                                    const lcgs_b200_frame* frame, lcgs_b200_stream stream);
 
@@ -239,7 +242,7 @@ LCGS_B200_API int lcgs_b200_read_image(lcgs_b200_ctx* ctx, const lcgs_b200_frame
 
 /* ---- per-stage timing (the reference has a single wall clock, app/main.cpp:225-226,317) ---- */
 
-#define LCGS_B200_NUM_STAGES 6 /* preprocess, scan, duplicate_keys, sort, ranges, blend */
+#define LCGS_B200_NUM_STAGES 7 /* preprocess, scan, depth_sort, duplicate_keys, sort, ranges, blend */
 LCGS_B200_API int lcgs_b200_set_profiling(lcgs_b200_ctx* ctx, int enabled);
 /* Synchronises; ms[i] = device time of stage i of the last whole-frame call. */
 LCGS_B200_API int lcgs_b200_stage_times(lcgs_b200_ctx* ctx, float ms[LCGS_B200_NUM_STAGES]);

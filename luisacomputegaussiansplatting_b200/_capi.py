@@ -11,8 +11,8 @@ import os
 from . import build as _build
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-NUM_STAGES = 6
-STAGES = ("preprocess", "scan", "duplicate_keys", "sort", "ranges", "blend")
+NUM_STAGES = 7
+STAGES = ("preprocess", "scan", "depth_sort", "duplicate_keys", "sort", "ranges", "blend")
 
 
 class LcgsError(RuntimeError):

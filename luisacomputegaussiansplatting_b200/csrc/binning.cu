@@ -85,6 +85,76 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Fused-path emission: Gaussians are visited in depth order (order[k], sorted depth bits skeys[k]);
+// rects are the packed tile rects preprocess wrote (x0 | y0<<16, w | h<<16), offsets2 the inclusive
+// sum of the counts in that order.  Same warp-cooperative expansion as above.
+__global__ void __launch_bounds__(256)
+    duplicate_keys_sorted_kernel(const uint32_t* __restrict__ d_m, uint32_t m_capacity, uint32_t gx, uint32_t row0,
+                                 const uint32_t* __restrict__ order, const uint32_t* __restrict__ skeys,
+                                 const uint2* __restrict__ rects, const uint32_t* __restrict__ offsets2,
+                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, size_t capacity)
+{
+    const int      lane        = threadIdx.x & 31;
+    const long     warp_global = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long     num_warps   = ((long)gridDim.x * blockDim.x) >> 5;
+    const unsigned FULL        = 0xFFFFFFFFu;
+    uint32_t       M           = *d_m;
+    if (M > m_capacity) M = m_capacity;
+
+    for (long base = warp_global * 32; base < M; base += num_warps * 32) {
+        const long k   = base + lane;
+        uint32_t   cnt = 0, x0 = 0, y0 = 0, w = 1, dbits = 0, incl = 0, idx = 0;
+        if (k < M) {
+            incl          = __ldg(offsets2 + k);
+            idx           = __ldg(order + k);
+            dbits         = __ldg(skeys + k);
+            const uint2 r = __ldg(rects + idx);
+            x0            = r.x & 0xFFFFu;
+            y0            = r.x >> 16;
+            w             = r.y & 0xFFFFu;
+            cnt           = w * (r.y >> 16);
+            if (w == 0) w = 1;
+        }
+        uint32_t excl = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) excl = (base > 0) ? __ldg(offsets2 + base - 1) : 0u;
+        uint32_t x = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, x, d);
+            if (lane >= d) x += y;
+        }
+        const uint32_t loc   = x - cnt;
+        const uint32_t total = __shfl_sync(FULL, x, 31);
+        for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            int            l = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t v = __shfl_sync(FULL, loc, l + step);
+                if (v <= p) l += step;
+            }
+            const uint32_t o_loc   = __shfl_sync(FULL, loc, l);
+            const uint32_t o_excl  = __shfl_sync(FULL, excl, l);
+            const uint32_t o_x0    = __shfl_sync(FULL, x0, l);
+            const uint32_t o_y0    = __shfl_sync(FULL, y0, l);
+            const uint32_t o_w     = __shfl_sync(FULL, w, l);
+            const uint32_t o_dbits = __shfl_sync(FULL, dbits, l);
+            const uint32_t o_idx   = __shfl_sync(FULL, idx, l);
+            if (p < total) {
+                const uint32_t j    = p - o_loc;
+                const uint32_t ry   = j / o_w;
+                const uint32_t rx   = j - ry * o_w;
+                const uint32_t tile = (o_x0 + rx) + (o_y0 + ry - row0) * gx;
+                const size_t   dst  = (size_t)o_excl + j;
+                if (dst < capacity) {
+                    keys[dst] = ((unsigned long long)tile << 32) | (unsigned long long)o_dbits;
+                    vals[dst] = o_idx;
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
     tile_ranges_kernel(const unsigned long long* __restrict__ keys, size_t n_host, const uint32_t* __restrict__ d_n,
                        size_t capacity, uint32_t* __restrict__ ranges, uint32_t num_tiles)
@@ -131,6 +201,23 @@ int launch_duplicate_keys(lcgs_b200_ctx* ctx, int P, int W, int H, const float* 
                                                           reinterpret_cast<const float2*>(means_2d), offsets, radii,
                                                           depth, reinterpret_cast<unsigned long long*>(keys), vals,
                                                           capacity);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, const uint32_t* order,
+                                 const uint32_t* skeys, const uint2* rects, const uint32_t* offsets2, uint64_t* keys,
+                                 uint32_t* vals, size_t capacity, int row0, cudaStream_t s)
+{
+    if (P <= 0) return LCGS_B200_OK;
+    const uint32_t gx           = (uint32_t)((W + 15) / 16);
+    const long     warps_needed = ((long)P + 31) / 32;
+    long           blocks       = (warps_needed + 7) / 8;
+    const long     max_blocks   = (long)ctx->num_sms * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    duplicate_keys_sorted_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, order, skeys, rects,
+                                                                 offsets2, reinterpret_cast<unsigned long long*>(keys), vals,
+                                                                 capacity);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }

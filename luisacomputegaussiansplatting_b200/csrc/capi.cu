@@ -2,6 +2,7 @@
 // per-stage entry points and the two whole-frame orchestrations.
 #include <math.h>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -91,23 +92,67 @@ static int check_frame_lists(lcgs_b200_ctx* ctx, const lcgs_b200_frame* fr)
     return LCGS_B200_OK;
 }
 
-// scan -> duplicate -> sort -> ranges -> blend, all on device-resident counts
+// Layout of the fused path's order workspace (all arrays have P entries).
+struct OrderWs {
+    uint2*    rects;
+    uint32_t *ckeys, *cvals, *skeys, *svals, *offsets2;
+};
+static OrderWs order_ws_views(lcgs_b200_ctx* ctx, int P)
+{
+    OrderWs o;
+    char*   base = (char*)ctx->order_ws.ptr;
+    const size_t n = (size_t)(P > 0 ? P : 1);
+    o.rects    = (uint2*)base;
+    o.ckeys    = (uint32_t*)(base + 8 * n);
+    o.cvals    = o.ckeys + n;
+    o.skeys    = o.cvals + n;
+    o.svals    = o.skeys + n;
+    o.offsets2 = o.svals + n;
+    return o;
+}
+
+// scan -> [depth sort of the Gaussians] -> duplicate -> sort -> ranges -> blend, all on device-resident counts.
+// depth_ordered = false: the reference's data flow (emit in index order, sort all key bits).
+// depth_ordered = true : sort the Gaussians by depth, emit in that order, stable-sort by tile bits only;
+//                        sorted keys / values / ranges are bit-identical (see scan.cu).
 static int splat_tail(lcgs_b200_ctx* ctx, int P, const lcgs_b200_frame* fr, const FrameGeom& g, const float* means_pix,
-                      cudaStream_t s)
+                      bool depth_ordered, cudaStream_t s)
 {
     int       rc;
     uint32_t* d_n = ctx->d_scalars + LCGS_SCALAR_NUM_RENDERED;
-    if ((rc = launch_scan(ctx, fr->tiles_touched, fr->point_offsets, (size_t)P, d_n, s))) return rc;
-    mark(ctx, s);
-    if ((rc = launch_duplicate_keys(ctx, P, g.W, g.H, means_pix, fr->point_offsets, fr->radii, fr->depth,
-                                    fr->point_list_keys_unsorted, fr->point_list_unsorted, fr->list_capacity, g.row0,
-                                    g.row1, s)))
-        return rc;
-    mark(ctx, s);
-    if ((rc = launch_sort(ctx, fr->point_list_keys_unsorted, fr->point_list_keys, fr->point_list_unsorted,
-                          fr->point_list, 0, d_n, fr->list_capacity, 0, g.end_bit, s)))
-        return rc;
-    mark(ctx, s);
+    uint32_t* d_m = ctx->d_scalars + LCGS_SCALAR_NUM_TOUCHING;
+    if (depth_ordered) {
+        const OrderWs o = order_ws_views(ctx, P);
+        if ((rc = launch_scan_compact(ctx, fr->tiles_touched, fr->depth, P, fr->point_offsets, o.ckeys, o.cvals, d_n, d_m, s)))
+            return rc;
+        mark(ctx, s);
+        // depth >= 0.2 > 0: the sign bit is clear, 31 key bits
+        if ((rc = launch_sort_u32(ctx, o.ckeys, o.skeys, o.cvals, o.svals, 0, d_m, (size_t)P, 0, 31, s))) return rc;
+        if ((rc = launch_scan_gather(ctx, o.svals, o.rects, d_m, P, o.offsets2, s))) return rc;
+        mark(ctx, s);
+        if ((rc = launch_duplicate_keys_sorted(ctx, d_m, P, g.W, o.svals, o.skeys, o.rects, o.offsets2,
+                                               fr->point_list_keys_unsorted, fr->point_list_unsorted, fr->list_capacity,
+                                               g.row0, s)))
+            return rc;
+        mark(ctx, s);
+        if ((rc = launch_sort(ctx, fr->point_list_keys_unsorted, fr->point_list_keys, fr->point_list_unsorted,
+                              fr->point_list, 0, d_n, fr->list_capacity, 32, g.end_bit, s)))
+            return rc;
+        mark(ctx, s);
+    } else {
+        if ((rc = launch_scan(ctx, fr->tiles_touched, fr->point_offsets, (size_t)P, d_n, s))) return rc;
+        mark(ctx, s);
+        mark(ctx, s);  // no depth sort in the reference's data flow
+        if ((rc = launch_duplicate_keys(ctx, P, g.W, g.H, means_pix, fr->point_offsets, fr->radii, fr->depth,
+                                        fr->point_list_keys_unsorted, fr->point_list_unsorted, fr->list_capacity, g.row0,
+                                        g.row1, s)))
+            return rc;
+        mark(ctx, s);
+        if ((rc = launch_sort(ctx, fr->point_list_keys_unsorted, fr->point_list_keys, fr->point_list_unsorted,
+                              fr->point_list, 0, d_n, fr->list_capacity, 0, g.end_bit, s)))
+            return rc;
+        mark(ctx, s);
+    }
     if ((rc = launch_ranges(ctx, fr->point_list_keys, 0, d_n, fr->list_capacity, fr->ranges, g.num_tiles, s))) return rc;
     mark(ctx, s);
     if ((rc = launch_blend(ctx, g.W, g.H, fr->bg_color, fr->ranges, fr->point_list, (const float4*)ctx->record_ws.ptr, d_n,
@@ -125,10 +170,12 @@ static int reserve_all(lcgs_b200_ctx* ctx, int P, size_t max_instances)
     int rc;
     if (P > 0) {
         if ((rc = ws_reserve(ctx, ctx->record_ws, (size_t)P * kRecordFloat4s * sizeof(float4)))) return rc;
-        if ((rc = ws_reserve(ctx, ctx->scan_ws, (((size_t)P + kScanTile - 1) / kScanTile) * sizeof(unsigned long long)))) return rc;
+        if ((rc = ws_reserve(ctx, ctx->scan_ws, (((size_t)P + 2047) / 2048) * 2 * sizeof(unsigned long long)))) return rc;
+        if ((rc = ws_reserve(ctx, ctx->order_ws, (size_t)P * 28))) return rc;
     }
-    if (max_instances > 0)
-        if ((rc = ws_reserve(ctx, ctx->sort_ws, sort_temp_bytes(max_instances)))) return rc;
+    const size_t sort_items = max_instances > (size_t)(P > 0 ? P : 0) ? max_instances : (size_t)(P > 0 ? P : 0);
+    if (sort_items > 0)
+        if ((rc = ws_reserve(ctx, ctx->sort_ws, sort_temp_bytes(sort_items)))) return rc;
     return LCGS_B200_OK;
 }
 
@@ -191,6 +238,7 @@ int lcgs_b200_ctx_destroy(lcgs_b200_ctx* ctx)
     if (ctx->scan_ws.ptr) cudaFree(ctx->scan_ws.ptr);
     if (ctx->sort_ws.ptr) cudaFree(ctx->sort_ws.ptr);
     if (ctx->record_ws.ptr) cudaFree(ctx->record_ws.ptr);
+    if (ctx->order_ws.ptr) cudaFree(ctx->order_ws.ptr);
     for (int i = 0; i < 16; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 3; i++)
@@ -440,7 +488,7 @@ int lcgs_b200_splat_forward(lcgs_b200_ctx* ctx, int P, const float* opacity, con
                                    (float4*)ctx->record_ws.ptr, s)))
         return rc;
     mark(ctx, s);
-    return splat_tail(ctx, P, fr, g, fr->means_2d, s);
+    return splat_tail(ctx, P, fr, g, fr->means_2d, false, s);
 }
 
 int lcgs_b200_render(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b200_view_params* vp,
@@ -462,9 +510,10 @@ int lcgs_b200_render(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b
     cudaStream_t s = as_stream(stream);
     ctx->ev_count  = 0;
     mark(ctx, s);
-    if ((rc = launch_preprocess_fused(ctx, sc, vp, fr, (float4*)ctx->record_ws.ptr, s))) return rc;
+    static const bool reference_flow = getenv("LCGS_REFERENCE_FLOW") != nullptr;  // debugging: emit in index order
+    if ((rc = launch_preprocess_fused(ctx, sc, vp, fr, (float4*)ctx->record_ws.ptr, order_ws_views(ctx, P).rects, s))) return rc;
     mark(ctx, s);
-    return splat_tail(ctx, P, fr, g, fr->means_2d, s);
+    return splat_tail(ctx, P, fr, g, fr->means_2d, !reference_flow, s);
 }
 
 int lcgs_b200_num_rendered(lcgs_b200_ctx* ctx, lcgs_b200_stream stream, int* num_rendered)

@@ -51,6 +51,7 @@ struct lcgs_b200_ctx {
     lcgs_b200::Workspace scan_ws;     // look-back tile status
     lcgs_b200::Workspace sort_ws;     // histograms + look-back status + ping-pong pair buffer
     lcgs_b200::Workspace record_ws;   // packed per-Gaussian blend records
+    lcgs_b200::Workspace order_ws;    // fused path: packed rects + compacted/sorted (depth, index) pairs + offsets
     // per-stage timing
     int          profiling  = 0;
     cudaEvent_t  ev[16];
@@ -62,7 +63,7 @@ struct lcgs_b200_ctx {
 };
 
 #define LCGS_SCALAR_NUM_RENDERED 0
-#define LCGS_SCALAR_OVERFLOW     1
+#define LCGS_SCALAR_NUM_TOUCHING 1   /* Gaussians with tiles_touched > 0 (fused path) */
 #define LCGS_SCALAR_SCAN_TICKET  2
 #define LCGS_SCALAR_SORT_TICKET  3   /* .. 3 + kMaxSortPasses - 1 */
 #define LCGS_SCALAR_DUP_TICKET   12
@@ -93,7 +94,17 @@ int ws_reserve(lcgs_b200_ctx* ctx, Workspace& ws, size_t bytes);
 
 // stage launchers (one group per .cu); all enqueue on `s` and return an lcgs_b200_status
 int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b200_view_params* vp,
-                            const lcgs_b200_frame* fr, float4* records, cudaStream_t s);
+                            const lcgs_b200_frame* fr, float4* records, uint2* rects, cudaStream_t s);
+int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const float* depth, int P, uint32_t* offsets,
+                        uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, cudaStream_t s);
+int launch_scan_gather(lcgs_b200_ctx* ctx, const uint32_t* order, const uint2* rects, const uint32_t* d_n, int capacity,
+                       uint32_t* offsets2, cudaStream_t s);
+int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, const uint32_t* order,
+                                 const uint32_t* skeys, const uint2* rects, const uint32_t* offsets2, uint64_t* keys,
+                                 uint32_t* vals, size_t capacity, int row0, cudaStream_t s);
+int launch_sort_u32(lcgs_b200_ctx* ctx, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
+                    uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
+                    cudaStream_t s);
 int launch_sh(lcgs_b200_ctx* ctx, int P, int deg, const float* cam_pos, const float* pos, const float* sh, float* color,
               cudaStream_t s);
 int launch_project(lcgs_b200_ctx* ctx, int P, const float* pos, const float* scale, const float* rotq,

@@ -32,6 +32,7 @@ struct PreprocessArgs {
     int32_t*     radii;
     uint32_t*    tiles;
     float4*      records;
+    uint2*       rects;  // packed tile rect of Gaussians that touch a tile: (x0 | y0<<16, w | h<<16)
 };
 
 constexpr int kPreThreads = 128;
@@ -91,6 +92,8 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
                 a.conic[3 * i + 2] = s.conic[2];
             }
             need = s.tiles > 0u;
+            if (need && a.rects)
+                a.rects[i] = make_uint2(s.rect.x0 | (s.rect.y0 << 16), (s.rect.x1 - s.rect.x0) | ((s.rect.y1 - s.rect.y0) << 16));
         } else {
             // defined behaviour for near-culled Gaussians (the reference leaves stale data, Q6)
             a.depth[i] = 0.0f;
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(256)
 static inline uint32_t div_up(long a, long b) { return (uint32_t)((a + b - 1) / b); }
 
 int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b200_view_params* vp,
-                            const lcgs_b200_frame* fr, float4* records, cudaStream_t s)
+                            const lcgs_b200_frame* fr, float4* records, uint2* rects, cudaStream_t s)
 {
     const int P = sc->num_gaussians;
     if (P <= 0) return LCGS_B200_OK;
@@ -256,7 +259,7 @@ int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const
     a.row0 = (uint32_t)fr->tile_row_begin;
     a.row1 = fr->tile_row_end < 0 ? a.gy : (uint32_t)fr->tile_row_end;
     a.means_2d = fr->means_2d; a.depth = fr->depth; a.conic = fr->conic; a.color = fr->color;
-    a.radii = fr->radii; a.tiles = fr->tiles_touched; a.records = records;
+    a.radii = fr->radii; a.tiles = fr->tiles_touched; a.records = records; a.rects = rects;
     preprocess_fused_kernel<<<div_up(P, kPreThreads), kPreThreads, 0, s>>>(a);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;

@@ -114,6 +114,218 @@ __global__ void __launch_bounds__(kScanThreads)
     }
 }
 
+// ---- fused-path variants ----------------------------------------------------------------------
+// The fused frame sorts the GAUSSIANS by depth first (3.7 M 8-byte pairs at C3) and emits the
+// instances in that order, so that the 17.8 M 12-byte instance pairs only need a stable sort by
+// their 13 tile bits (2 radix passes instead of 5).  A stable sort by tile of a list ordered by
+// (depth, index) is exactly the order of a stable 64-bit sort of (tile<<32 | depth) keys emitted in
+// index order, so sorted keys, sorted values and ranges are bit-identical to the reference's.
+//
+// scan_compact_kernel: point_offsets (inclusive sum of tiles_touched, the reference's output) AND a
+// stable compaction of the Gaussians that touch a tile into (depth bits, index) pairs.
+// scan_gather_kernel: inclusive sum of the tile counts taken in depth order (offsets of the emission).
+
+struct ScanPair {
+    uint32_t a, b;
+};
+
+// block-wide exclusive scan of two values per thread (warp shuffles + one shared-memory hop);
+// returns the exclusive prefix and the block totals
+__device__ __forceinline__ ScanPair block_scan_pair(ScanPair v, ScanPair* s_warp /* [8] */, ScanPair* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t  xa = v.a, xb = v.b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ya = __shfl_up_sync(0xFFFFFFFFu, xa, d), yb = __shfl_up_sync(0xFFFFFFFFu, xb, d);
+        if (lane >= d) { xa += ya; xb += yb; }
+    }
+    if (lane == 31) s_warp[warp] = ScanPair{ xa, xb };
+    __syncthreads();
+    ScanPair pre{ 0, 0 }, tot{ 0, 0 };
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; w++) {
+        const ScanPair x = s_warp[w];
+        if (w < warp) { pre.a += x.a; pre.b += x.b; }
+        tot.a += x.a; tot.b += x.b;
+    }
+    __syncthreads();
+    *total = tot;
+    return ScanPair{ pre.a + xa - v.a, pre.b + xb - v.b };
+}
+
+// decoupled look-back of one chained sum by one thread; publishes aggregate then inclusive
+__device__ __forceinline__ uint32_t lookback_u32(unsigned long long* status, uint32_t tile, uint32_t tile_sum)
+{
+    uint32_t prefix = 0;
+    if (tile > 0) {
+        st_status(status + tile, kFlagAggregate | tile_sum);
+        int p = (int)tile - 1;
+        for (;;) {
+            unsigned long long st;
+            do { st = ld_status(status + p); } while ((st >> 32) == 0ull);
+            prefix += (uint32_t)st;
+            if ((st >> 32) == 2ull) break;
+            --p;
+        }
+    }
+    st_status(status + tile, kFlagInclusive | (unsigned long long)(prefix + tile_sum));
+    return prefix;
+}
+
+constexpr int kCompactItems = 8;                          // per thread
+constexpr int kCompactTile  = kScanThreads * kCompactItems;  // 2048 Gaussians per CTA
+
+__global__ void __launch_bounds__(kScanThreads)
+    scan_compact_kernel(const uint32_t* __restrict__ tiles_touched, const float* __restrict__ depth, uint32_t n,
+                        uint32_t num_tiles, uint32_t* __restrict__ offsets, uint32_t* __restrict__ ckeys,
+                        uint32_t* __restrict__ cvals, unsigned long long* status_sum, unsigned long long* status_cnt,
+                        uint32_t* ticket, uint32_t* d_total, uint32_t* d_count)
+{
+    __shared__ uint32_t s_tile;
+    __shared__ ScanPair s_warp[kScanThreads / 32];
+    __shared__ uint32_t s_prefix[2];
+    const int tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= num_tiles) return;
+    // blocked arrangement: thread t owns items [base + t*8, +8) -> two 16-byte loads
+    const uint32_t e0 = tile * kCompactTile + tid * kCompactItems;
+    uint32_t       v[kCompactItems];
+    if (e0 + kCompactItems <= n) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(tiles_touched + e0));
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(tiles_touched + e0) + 1);
+        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kCompactItems; k++) v[k] = (e0 + k < n) ? __ldg(tiles_touched + e0 + k) : 0u;
+    }
+    ScanPair mine{ 0, 0 };
+#pragma unroll
+    for (int k = 0; k < kCompactItems; k++) {
+        mine.a += v[k];
+        mine.b += v[k] > 0u ? 1u : 0u;
+    }
+    ScanPair       tot;
+    const ScanPair excl = block_scan_pair(mine, s_warp, &tot);
+    if (tid == 0) s_prefix[0] = lookback_u32(status_sum, tile, tot.a);
+    if (tid == 32) s_prefix[1] = lookback_u32(status_cnt, tile, tot.b);
+    __syncthreads();
+    uint32_t sum = s_prefix[0] + excl.a, cnt = s_prefix[1] + excl.b;
+    if (tile == num_tiles - 1 && tid == 0) {
+        *d_total = s_prefix[0] + tot.a;
+        *d_count = s_prefix[1] + tot.b;
+    }
+    uint32_t out[kCompactItems];
+#pragma unroll
+    for (int k = 0; k < kCompactItems; k++) {
+        sum += v[k];
+        out[k] = sum;
+        if (v[k] > 0u) {  // stable compaction: slots are handed out in index order
+            ckeys[cnt] = __float_as_uint(__ldg(depth + e0 + k));
+            cvals[cnt] = e0 + k;
+            cnt++;
+        }
+    }
+    if (e0 + kCompactItems <= n) {
+        reinterpret_cast<uint4*>(offsets + e0)[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        reinterpret_cast<uint4*>(offsets + e0)[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kCompactItems; k++)
+            if (e0 + k < n) offsets[e0 + k] = out[k];
+    }
+}
+
+// offsets2[k] = inclusive sum over k of the tile count of Gaussian order[k] (count = rect area)
+__global__ void __launch_bounds__(kScanThreads)
+    scan_gather_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rects, const uint32_t* __restrict__ d_n,
+                       uint32_t capacity, uint32_t* __restrict__ offsets2, unsigned long long* status, uint32_t* ticket)
+{
+    __shared__ uint32_t s_tile;
+    __shared__ ScanPair s_warp[kScanThreads / 32];
+    __shared__ uint32_t s_prefix;
+    const int      tid       = threadIdx.x;
+    uint32_t       n         = *d_n;
+    if (n > capacity) n = capacity;
+    const uint32_t num_tiles = (n + kCompactTile - 1) / kCompactTile;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) return;
+        // striped arrangement: coalesced index loads, the rect gathers hit L2
+        uint32_t v[kCompactItems];
+#pragma unroll
+        for (int k = 0; k < kCompactItems; k++) {
+            const uint32_t e = tile * kCompactTile + k * kScanThreads + tid;
+            v[k]             = 0u;
+            if (e < n) {
+                const uint2 r = __ldg(rects + __ldg(order + e));
+                v[k]          = (r.y & 0xFFFFu) * (r.y >> 16);
+            }
+        }
+        // scan in element order: element e = tile*2048 + k*256 + tid -> k-major
+        ScanPair tot;
+        uint32_t excl[kCompactItems], carry = 0;
+#pragma unroll
+        for (int k = 0; k < kCompactItems; k++) {
+            const ScanPair x = block_scan_pair(ScanPair{ v[k], 0u }, s_warp, &tot);
+            excl[k]          = carry + x.a;
+            carry += tot.a;
+        }
+        if (tid == 0) s_prefix = lookback_u32(status, tile, carry);
+        __syncthreads();
+        const uint32_t pre = s_prefix;
+#pragma unroll
+        for (int k = 0; k < kCompactItems; k++) {
+            const uint32_t e = tile * kCompactTile + k * kScanThreads + tid;
+            if (e < n) offsets2[e] = pre + excl[k] + v[k];
+        }
+    }
+}
+
+int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const float* depth, int P, uint32_t* offsets,
+                        uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, cudaStream_t s)
+{
+    if (P <= 0) {
+        LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint32_t), s));
+        LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s));
+        return LCGS_B200_OK;
+    }
+    LCGS_REQUIRE(ctx, ((((uintptr_t)tiles_touched) | ((uintptr_t)offsets)) & 15) == 0, "scan: tiles_touched / point_offsets must be 16-byte aligned");
+    const uint32_t tiles = (uint32_t)(((size_t)P + kCompactTile - 1) / kCompactTile);
+    int            rc    = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * 2 * sizeof(unsigned long long));
+    if (rc) return rc;
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->scan_ws.ptr, 0, (size_t)tiles * 2 * sizeof(unsigned long long), s));
+    uint32_t* ticket = ctx->d_scalars + LCGS_SCALAR_SCAN_TICKET;
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
+    auto* st = (unsigned long long*)ctx->scan_ws.ptr;
+    scan_compact_kernel<<<tiles, kScanThreads, 0, s>>>(tiles_touched, depth, (uint32_t)P, tiles, offsets, ckeys, cvals, st,
+                                                       st + tiles, ticket, d_total, d_count);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+int launch_scan_gather(lcgs_b200_ctx* ctx, const uint32_t* order, const uint2* rects, const uint32_t* d_n, int capacity,
+                       uint32_t* offsets2, cudaStream_t s)
+{
+    if (capacity <= 0) return LCGS_B200_OK;
+    const uint32_t tiles = (uint32_t)(((size_t)capacity + kCompactTile - 1) / kCompactTile);
+    int            rc    = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * 2 * sizeof(unsigned long long));
+    if (rc) return rc;
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->scan_ws.ptr, 0, (size_t)tiles * sizeof(unsigned long long), s));
+    uint32_t* ticket = ctx->d_scalars + LCGS_SCALAR_SCAN_TICKET;
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
+    const uint32_t blocks = tiles < (uint32_t)ctx->num_sms * 8u ? tiles : (uint32_t)ctx->num_sms * 8u;
+    scan_gather_kernel<<<blocks, kScanThreads, 0, s>>>(order, rects, d_n, (uint32_t)capacity, offsets2,
+                                                      (unsigned long long*)ctx->scan_ws.ptr, ticket);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
 int launch_scan(lcgs_b200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t n, uint32_t* d_total, cudaStream_t s)
 {
     if (n == 0) {

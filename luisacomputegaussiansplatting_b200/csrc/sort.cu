@@ -55,6 +55,11 @@ __device__ __forceinline__ uint32_t key_digit_hi(unsigned long long key, int shi
     return ((uint32_t)(key >> 32) >> (shift - 32)) & mask;  // shift >= 32
 }
 
+__device__ __forceinline__ uint32_t key_digit(uint32_t key, int shift, uint32_t mask) { return (key >> shift) & mask; }
+__device__ __forceinline__ uint32_t key_digit_hi(uint32_t key, int, uint32_t) { return key; }  // unreachable (shift < 32)
+__device__ __forceinline__ unsigned long long key_ones(unsigned long long) { return ~0ull; }
+__device__ __forceinline__ uint32_t           key_ones(uint32_t) { return ~0u; }
+
 struct SortPassInfo {
     int      num_passes;
     int      radix_bits;
@@ -63,8 +68,9 @@ struct SortPassInfo {
 };
 
 // ---- upfront histogram of every pass's digit ---------------------------------------------------
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-    radix_histogram_kernel(const unsigned long long* __restrict__ keys, size_t n_host, const uint32_t* __restrict__ d_n,
+    radix_histogram_kernel(const KeyT* __restrict__ keys, size_t n_host, const uint32_t* __restrict__ d_n,
                            size_t capacity, uint32_t* __restrict__ hist, const __grid_constant__ SortPassInfo info)
 {
     __shared__ uint32_t s_hist[kMaxSortPasses * kMaxRadix];
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(256)
     const size_t n      = resolve_n(n_host, d_n, capacity);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-        const unsigned long long key = __ldg(keys + k);
+        const KeyT key = __ldg(keys + k);
 #pragma unroll
         for (int p = 0; p < kMaxSortPasses; p++)
             if (p < info.num_passes)
@@ -115,16 +121,31 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 //   s_vals [TILE]         u32  tile's values in tile-sorted order
 //   s_wh   [WARPS][RADIX] u32  per-warp digit counters, then each warp's first slot per digit
 //   s_base [RADIX]        u32  global position of the digit's first pair minus its first tile slot
-template <int THREADS, int ITEMS, int RBITS>
+template <typename KeyT, int THREADS, int ITEMS, int RBITS>
 constexpr size_t sweep_smem_bytes()
 {
-    return (size_t)THREADS * ITEMS * 12 + (size_t)(THREADS / 32) * (1 << RBITS) * 4 + (size_t)(1 << RBITS) * 4 + (THREADS / 32) * 4 +
+    return (size_t)THREADS * ITEMS * (sizeof(KeyT) + 4) + (size_t)(THREADS / 32) * (1 << RBITS) * 4 + (size_t)(1 << RBITS) * 4 + (THREADS / 32) * 4 +
            64;
 }
 
-template <int THREADS, int ITEMS, int RBITS, int MIN_BLOCKS>
+// lanes holding the same digit as this lane: MATCH.ANY, or RBITS ballots (+1 for the "invalid" flag)
+template <int RBITS, bool USE_MATCH>
+__device__ __forceinline__ unsigned digit_peers(uint32_t d)
+{
+    if (USE_MATCH) return __match_any_sync(0xFFFFFFFFu, d);
+    unsigned peers = 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = 0; b <= RBITS; b++) {
+        const bool     bit = (d >> b) & 1u;
+        const unsigned m   = __ballot_sync(0xFFFFFFFFu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
+template <typename KeyT, int THREADS, int ITEMS, int RBITS, int MIN_BLOCKS, bool USE_MATCH>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
-    onesweep_pass_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
+    onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                          const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
                          const uint32_t* __restrict__ d_n, size_t capacity, const uint32_t* __restrict__ hist /* [RADIX] */,
                          uint32_t* status /* [tiles][RADIX] */, uint32_t* ticket, int shift, uint32_t mask,
@@ -136,7 +157,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit");
     static_assert((WARPS * RADIX) % THREADS == 0, "counter zeroing");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* const s_keys   = reinterpret_cast<unsigned long long*>(smem_raw);
+    KeyT* const               s_keys   = reinterpret_cast<KeyT*>(smem_raw);
     uint32_t* const           s_vals   = reinterpret_cast<uint32_t*>(s_keys + TILE);
     uint32_t* const           s_wh     = s_vals + TILE;
     uint32_t* const           s_base   = s_wh + WARPS * RADIX;
@@ -153,7 +174,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const bool     hi_word   = shift >= 32;  // uniform: the digit lives entirely in the key's high word
     uint32_t* const my_hist  = s_wh + warp * RADIX;
 
-    auto digit_of = [&](unsigned long long k) -> uint32_t {
+    auto digit_of = [&](KeyT k) -> uint32_t {
         return hi_word ? key_digit_hi(k, shift, mask) : key_digit(k, shift, mask);
     };
     auto tile_valid = [&](uint32_t t) -> uint32_t {
@@ -174,17 +195,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     __syncthreads();
     uint32_t tile = s_ticket[0];
 
-    unsigned long long key[ITEMS];
+    KeyT key[ITEMS];
     auto load_keys = [&](uint32_t t) {
         if (t >= num_tiles) return;
-        const unsigned long long* src = keys_in + (size_t)t * TILE + q0;
+        const KeyT* src = keys_in + (size_t)t * TILE + q0;
         const uint32_t            nv  = tile_valid(t);
         if (nv == (uint32_t)TILE) {
 #pragma unroll
             for (int j = 0; j < ITEMS; j++) key[j] = __ldg(src + 32 * j);
         } else {
 #pragma unroll
-            for (int j = 0; j < ITEMS; j++) key[j] = (q0 + 32 * j < nv) ? __ldg(src + 32 * j) : ~0ull;
+            for (int j = 0; j < ITEMS; j++) key[j] = (q0 + 32 * j < nv) ? __ldg(src + 32 * j) : key_ones(KeyT());
         }
     };
     load_keys(tile);
@@ -208,7 +229,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 #pragma unroll
             for (int j = 0; j < ITEMS; j++) {
                 const uint32_t d     = digit_of(key[j]);
-                const unsigned peers = __match_any_sync(FULLM, d);
+                const unsigned peers = digit_peers<RBITS, USE_MATCH>(d);
                 const unsigned lower = peers & lt_mask;
                 const uint32_t pre   = my_hist[d];
                 __syncwarp();
@@ -221,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             for (int j = 0; j < ITEMS; j++) {
                 const bool     valid = q0 + 32 * j < nvalid;
                 const uint32_t d     = valid ? digit_of(key[j]) : (uint32_t)RADIX;
-                const unsigned peers = __match_any_sync(FULLM, d);
+                const unsigned peers = digit_peers<RBITS, USE_MATCH>(d);
                 const unsigned lower = peers & lt_mask;
                 uint32_t       pre   = 0;
                 if (valid) pre = my_hist[d];
@@ -236,16 +257,18 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         const uint32_t next_tile = s_ticket[1];
 
         // ---- per digit (thread d): tile histogram, early publish, first look-back window ---------
+        constexpr bool  kCntInRegs = WARPS <= 16;  // otherwise re-read the counters instead of holding them
         uint32_t        tile_count = 0;
-        uint32_t        cnt[WARPS];
+        uint32_t        cnt[kCntInRegs ? WARPS : 1];
         uint32_t        st[kLookbackWindow];
         uint32_t* const my_status = status + (size_t)tile * RADIX + tid;
         int             p         = (int)tile - 1;
         if (is_digit) {
 #pragma unroll
             for (int w = 0; w < WARPS; w++) {
-                cnt[w] = s_wh[w * RADIX + tid];
-                tile_count += cnt[w];
+                const uint32_t c = s_wh[w * RADIX + tid];
+                if (kCntInRegs) cnt[w] = c;
+                tile_count += c;
             }
             if (tile > 0) st_relaxed_u32(my_status, kStatusAggregate | tile_count);
             // the predecessors' status words are requested now and consumed after the key scatter
@@ -258,8 +281,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             uint32_t run = tile_start;
 #pragma unroll
             for (int w = 0; w < WARPS; w++) {
+                const uint32_t c      = kCntInRegs ? cnt[w] : s_wh[w * RADIX + tid];
                 s_wh[w * RADIX + tid] = run;
-                run += cnt[w];
+                run += c;
             }
         }
         __syncthreads();
@@ -319,9 +343,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         for (int j = 0; j < ITEMS; j++) {
             const uint32_t q = tid + j * THREADS;
             if (full || q < nvalid) {
-                const unsigned long long k = s_keys[q];
-                dst[j]                     = s_base[digit_of(k)] + q;
-                keys_out[dst[j]]           = k;
+                const KeyT k     = s_keys[q];
+                dst[j]           = s_base[digit_of(k)] + q;
+                keys_out[dst[j]] = k;
             }
         }
 #pragma unroll
@@ -345,8 +369,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     }
 }
 
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-    copy_pairs_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
+    copy_pairs_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                       const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
                       const uint32_t* __restrict__ d_n, size_t capacity)
 {
@@ -358,42 +383,67 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-typedef void (*SweepKernel)(const unsigned long long*, unsigned long long*, const uint32_t*, uint32_t*, size_t, const uint32_t*,
-                            size_t, const uint32_t*, uint32_t*, uint32_t*, int, uint32_t, unsigned long long*);
+template <typename KeyT>
 struct SweepVariant {
-    SweepKernel kernel;
+    void (*kernel)(const KeyT*, KeyT*, const uint32_t*, uint32_t*, size_t, const uint32_t*, size_t, const uint32_t*, uint32_t*,
+                   uint32_t*, int, uint32_t, unsigned long long*);
     int         threads, tile, radix_bits, blocks_per_sm;
     size_t      smem;
     const char* name;
 };
-#define LCGS_SWEEP(T, I, R, B) \
-    { onesweep_pass_kernel<T, I, R, B>, T, T * I, R, B, sweep_smem_bytes<T, I, R>(), #T "x" #I " r" #R " " #B "/SM" }
-static const SweepVariant kSweepVariants[] = {
-    LCGS_SWEEP(512, 8, 9, 2),  // default: 9-bit digits, 2 CTAs x 16 warps per SM
-    LCGS_SWEEP(512, 8, 8, 2),
-    LCGS_SWEEP(256, 16, 8, 2),
-    LCGS_SWEEP(256, 16, 8, 3),
-    LCGS_SWEEP(512, 12, 9, 1),
-    LCGS_SWEEP(1024, 4, 9, 1),
-    LCGS_SWEEP(512, 6, 9, 2),
-    LCGS_SWEEP(256, 8, 8, 4),
-};
-constexpr int kNumSweepVariants = (int)(sizeof(kSweepVariants) / sizeof(kSweepVariants[0]));
-constexpr int kMinSweepTile     = 2048;
+#define LCGS_SWEEP(K, T, I, R, B, M) \
+    { onesweep_pass_kernel<K, T, I, R, B, M>, T, T * I, R, B, sweep_smem_bytes<K, T, I, R>(), #T "x" #I " r" #R " " #B "/SM" }
 
+// (tile<<32 | depth) instance keys; LCGS_SORT_VARIANT selects another geometry (tuning only)
+static const SweepVariant<unsigned long long> kSweep64[] = {
+    LCGS_SWEEP(unsigned long long, 512, 8, 9, 2, true),  // default: 9-bit digits, 2 CTAs x 16 warps per SM
+    LCGS_SWEEP(unsigned long long, 512, 8, 8, 2, true),
+    LCGS_SWEEP(unsigned long long, 256, 16, 8, 2, true),
+    LCGS_SWEEP(unsigned long long, 256, 16, 8, 3, true),
+    LCGS_SWEEP(unsigned long long, 512, 12, 9, 1, true),
+    LCGS_SWEEP(unsigned long long, 1024, 8, 9, 1, true),
+    LCGS_SWEEP(unsigned long long, 512, 6, 9, 2, true),
+    LCGS_SWEEP(unsigned long long, 256, 8, 8, 4, true),
+};
+// 32-bit depth keys of the per-Gaussian sort
+static const SweepVariant<uint32_t> kSweep32[] = {
+    LCGS_SWEEP(uint32_t, 512, 8, 9, 2, true),
+    LCGS_SWEEP(uint32_t, 512, 8, 8, 2, true),
+    LCGS_SWEEP(uint32_t, 256, 16, 8, 3, true),
+    LCGS_SWEEP(uint32_t, 512, 4, 9, 3, true),
+    LCGS_SWEEP(uint32_t, 256, 8, 8, 4, true),
+};
+constexpr int kMinSweepTile = 2048;
+
+template <typename KeyT>
+struct SweepTable;
+template <>
+struct SweepTable<unsigned long long> {
+    static const SweepVariant<unsigned long long>* table() { return kSweep64; }
+    static int count() { return (int)(sizeof(kSweep64) / sizeof(kSweep64[0])); }
+    static const char* env() { return "LCGS_SORT_VARIANT"; }
+};
+template <>
+struct SweepTable<uint32_t> {
+    static const SweepVariant<uint32_t>* table() { return kSweep32; }
+    static int count() { return (int)(sizeof(kSweep32) / sizeof(kSweep32[0])); }
+    static const char* env() { return "LCGS_SORT32_VARIANT"; }
+};
+
+template <typename KeyT>
 static int sweep_variant_index()
 {
     static int idx = -1;
     if (idx < 0) {
         idx           = 0;
-        const char* e = getenv("LCGS_SORT_VARIANT");
-        if (e && atoi(e) >= 0 && atoi(e) < kNumSweepVariants) idx = atoi(e);
+        const char* e = getenv(SweepTable<KeyT>::env());
+        if (e && atoi(e) >= 0 && atoi(e) < SweepTable<KeyT>::count()) idx = atoi(e);
     }
     return idx;
 }
 
 // workspace layout: [hist: passes*512 u32][status: passes*tiles*RADIX u32][tmp keys][tmp vals]
-static size_t sort_ws_layout(size_t n, size_t* off_status, size_t* off_keys, size_t* off_vals)
+static size_t sort_ws_layout(size_t n, size_t key_bytes, size_t* off_status, size_t* off_keys, size_t* off_vals)
 {
     const size_t tiles = (n + kMinSweepTile - 1) / kMinSweepTile;
     size_t       off   = 0;
@@ -403,7 +453,7 @@ static size_t sort_ws_layout(size_t n, size_t* off_status, size_t* off_keys, siz
     off += (size_t)kMaxSortPasses * tiles * kMaxRadix * sizeof(uint32_t);
     off = (off + 255) & ~(size_t)255;
     if (off_keys) *off_keys = off;
-    off += n * sizeof(uint64_t);
+    off += n * key_bytes;
     off = (off + 255) & ~(size_t)255;
     if (off_vals) *off_vals = off;
     off += n * sizeof(uint32_t);
@@ -411,70 +461,70 @@ static size_t sort_ws_layout(size_t n, size_t* off_status, size_t* off_keys, siz
     return off;
 }
 
-size_t sort_temp_bytes(size_t n) { return sort_ws_layout(n, nullptr, nullptr, nullptr); }
+size_t sort_temp_bytes(size_t n) { return sort_ws_layout(n, sizeof(uint64_t), nullptr, nullptr, nullptr); }
 
-int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
-                uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
-                cudaStream_t s)
+template <typename KeyT>
+static int launch_sort_t(lcgs_b200_ctx* ctx, const KeyT* kin, KeyT* kout, const uint32_t* vals_in, uint32_t* vals_out,
+                         size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit, uint32_t* ticket,
+                         bool record_events, cudaStream_t s)
 {
-    LCGS_REQUIRE(ctx, begin_bit >= 0 && end_bit <= 64 && begin_bit <= end_bit, "sort: bad bit range");
+    constexpr int kKeyBits = (int)sizeof(KeyT) * 8;
+    LCGS_REQUIRE(ctx, begin_bit >= 0 && end_bit <= kKeyBits && begin_bit <= end_bit, "sort: bad bit range");
     const size_t bound = d_n ? capacity : n_host;  // upper bound on the number of pairs
     if (bound == 0) return LCGS_B200_OK;
     LCGS_REQUIRE(ctx, bound <= (size_t)kStatusValueMask, "sort: more than 2^30-1 pairs");
     if (!d_n) capacity = n_host;
 
-    const SweepVariant& var   = kSweepVariants[sweep_variant_index()];
-    const int           bits  = end_bit - begin_bit;
-    const int           rbits = var.radix_bits;
-    SortPassInfo        info;
+    const int                 vi    = sweep_variant_index<KeyT>();
+    const SweepVariant<KeyT>& var   = SweepTable<KeyT>::table()[vi];
+    const int                 bits  = end_bit - begin_bit;
+    const int                 rbits = var.radix_bits;
+    SortPassInfo              info;
     info.radix_bits = rbits;
     info.num_passes = (bits + rbits - 1) / rbits;
     LCGS_REQUIRE(ctx, info.num_passes <= kMaxSortPasses, "sort: too many passes");
     for (int p = 0; p < kMaxSortPasses; p++) {
         const int lo  = begin_bit + p * rbits;
         const int w   = (p < info.num_passes) ? ((end_bit - lo) < rbits ? (end_bit - lo) : rbits) : 0;
-        info.shift[p] = lo < 64 ? lo : 0;
+        info.shift[p] = lo < kKeyBits ? lo : 0;
         info.mask[p]  = w > 0 ? ((1u << w) - 1u) : 0u;
     }
 
-    const auto* kin  = reinterpret_cast<const unsigned long long*>(keys_in);
-    auto*       kout = reinterpret_cast<unsigned long long*>(keys_out);
     const unsigned grid_stride_blocks = (unsigned)(((bound + 1023) / 1024) < (size_t)ctx->num_sms * 8
                                                        ? ((bound + 1023) / 1024)
                                                        : (size_t)ctx->num_sms * 8);
     if (info.num_passes == 0) {
-        copy_pairs_kernel<<<grid_stride_blocks, 256, 0, s>>>(kin, kout, vals_in, vals_out, n_host, d_n, capacity);
+        copy_pairs_kernel<KeyT><<<grid_stride_blocks, 256, 0, s>>>(kin, kout, vals_in, vals_out, n_host, d_n, capacity);
         LCGS_CUDA_CHECK(ctx, cudaGetLastError());
         return LCGS_B200_OK;
     }
 
     size_t       off_status, off_keys, off_vals;
-    const size_t bytes = sort_ws_layout(bound, &off_status, &off_keys, &off_vals);
+    const size_t bytes = sort_ws_layout(bound, sizeof(KeyT), &off_status, &off_keys, &off_vals);
     int          rc    = ws_reserve(ctx, ctx->sort_ws, bytes);
     if (rc) return rc;
     char*        ws       = (char*)ctx->sort_ws.ptr;
     uint32_t*    hist     = (uint32_t*)ws;
     uint32_t*    status   = (uint32_t*)(ws + off_status);
-    auto*        tmp_keys = (unsigned long long*)(ws + off_keys);
+    KeyT*        tmp_keys = (KeyT*)(ws + off_keys);
     uint32_t*    tmp_vals = (uint32_t*)(ws + off_vals);
     const int    radix    = 1 << rbits;
     const size_t tiles    = (bound + var.tile - 1) / var.tile;
-    uint32_t*    ticket   = ctx->d_scalars + LCGS_SCALAR_SORT_TICKET;
 
     // zero histograms + look-back status (contiguous) and the tickets
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ws, 0, off_status + (size_t)info.num_passes * tiles * radix * sizeof(uint32_t), s));
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, kMaxSortPasses * sizeof(uint32_t), s));
 
-    const bool prof = ctx->profiling && ctx->ev_sort[0];
+    const bool prof = record_events && ctx->profiling && ctx->ev_sort[0];
     if (prof) cudaEventRecord(ctx->ev_sort[0], s);
-    radix_histogram_kernel<<<grid_stride_blocks, 256, 0, s>>>(kin, n_host, d_n, capacity, hist, info);
+    radix_histogram_kernel<KeyT><<<grid_stride_blocks, 256, 0, s>>>(kin, n_host, d_n, capacity, hist, info);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     if (prof) cudaEventRecord(ctx->ev_sort[1], s);
 
-    static bool smem_attr_set[kNumSweepVariants] = {};  // opt in to > 48 KB of dynamic shared memory once per process
-    if (!smem_attr_set[sweep_variant_index()]) {
+    static bool smem_attr_set[16] = {};  // opt in to > 48 KB of dynamic shared memory once per process
+    if (!smem_attr_set[vi]) {
         LCGS_CUDA_CHECK(ctx, cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
-        smem_attr_set[sweep_variant_index()] = true;
+        smem_attr_set[vi] = true;
     }
     const size_t   max_ctas     = (size_t)ctx->num_sms * var.blocks_per_sm;
     const unsigned sweep_blocks = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
@@ -498,12 +548,12 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
                     h[10], h[0] / h[10], h[1] / h[10], h[2] / h[10], h[3] / h[10], h[4] / h[10], h[5] / h[10],
                     (double)h[8] / h[10], (double)h[9] / h[10]);
     }
-    const unsigned long long* src_k = kin;
-    const uint32_t*           src_v = vals_in;
+    const KeyT*     src_k = kin;
+    const uint32_t* src_v = vals_in;
     for (int p = 0; p < info.num_passes; p++) {
-        const bool          to_out = ((info.num_passes - 1 - p) % 2) == 0;
-        unsigned long long* dst_k  = to_out ? kout : tmp_keys;
-        uint32_t*           dst_v  = to_out ? vals_out : tmp_vals;
+        const bool to_out = ((info.num_passes - 1 - p) % 2) == 0;
+        KeyT*      dst_k  = to_out ? kout : tmp_keys;
+        uint32_t*  dst_v  = to_out ? vals_out : tmp_vals;
         var.kernel<<<sweep_blocks, var.threads, var.smem, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
                                                               hist + (size_t)p * radix, status + (size_t)p * tiles * radix,
                                                               ticket + p, info.shift[p], info.mask[p], dbg);
@@ -517,6 +567,24 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
         ctx->ev_sort_valid = 1;
     }
     return LCGS_B200_OK;
+}
+
+int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
+                uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
+                cudaStream_t s)
+{
+    return launch_sort_t<unsigned long long>(ctx, reinterpret_cast<const unsigned long long*>(keys_in),
+                                             reinterpret_cast<unsigned long long*>(keys_out), vals_in, vals_out, n_host, d_n,
+                                             capacity, begin_bit, end_bit, ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, true, s);
+}
+
+// per-Gaussian (depth bits, index) sort of the fused path; shares the context's sort workspace
+int launch_sort_u32(lcgs_b200_ctx* ctx, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
+                    uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
+                    cudaStream_t s)
+{
+    return launch_sort_t<uint32_t>(ctx, keys_in, keys_out, vals_in, vals_out, n_host, d_n, capacity, begin_bit, end_bit,
+                                   ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, false, s);
 }
 
 }  // namespace lcgs_b200
