@@ -404,6 +404,10 @@ static const SweepVariant<unsigned long long> kSweep64[] = {
     LCGS_SWEEP(unsigned long long, 1024, 8, 9, 1, true),
     LCGS_SWEEP(unsigned long long, 512, 6, 9, 2, true),
     LCGS_SWEEP(unsigned long long, 256, 8, 8, 4, true),
+    LCGS_SWEEP(unsigned long long, 512, 8, 7, 2, true),   // 8: 7-bit digits (13 tile bits = 7 + 6)
+    LCGS_SWEEP(unsigned long long, 256, 16, 7, 3, true),  // 9
+    LCGS_SWEEP(unsigned long long, 256, 16, 7, 2, true),  // 10
+    LCGS_SWEEP(unsigned long long, 512, 12, 7, 1, true),  // 11
 };
 // 32-bit depth keys of the per-Gaussian sort
 static const SweepVariant<uint32_t> kSweep32[] = {
