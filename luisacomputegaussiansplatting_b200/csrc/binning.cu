@@ -92,8 +92,17 @@ __global__ void __launch_bounds__(256)
     duplicate_keys_sorted_kernel(const uint32_t* __restrict__ d_m, uint32_t m_capacity, uint32_t gx, uint32_t row0,
                                  const uint32_t* __restrict__ order, const uint32_t* __restrict__ skeys,
                                  const uint2* __restrict__ rects, const uint32_t* __restrict__ offsets2,
-                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, size_t capacity)
+                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, size_t capacity,
+                                 const __grid_constant__ SortDigits digits)
 {
+    // digit histograms of the tile bits of the emitted keys (two passes at most: the tile sort then skips
+    // its histogram kernel).  Consecutive lanes emit consecutive tiles of one Gaussian, so the upper digit
+    // is warp-aggregated with match_any.
+    __shared__ uint32_t s_hist[2 * 512];
+    const bool          do_hist = digits.hist != nullptr;
+    const int           nbins   = do_hist ? (digits.num_passes << digits.radix_bits) : 0;
+    for (int k = threadIdx.x; k < nbins; k += blockDim.x) s_hist[k] = 0u;
+    if (do_hist) __syncthreads();
     const int      lane        = threadIdx.x & 31;
     const long     warp_global = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long     num_warps   = ((long)gridDim.x * blockDim.x) >> 5;
@@ -149,8 +158,23 @@ __global__ void __launch_bounds__(256)
                 if (dst < capacity) {
                     keys[dst] = ((unsigned long long)tile << 32) | (unsigned long long)o_dbits;
                     vals[dst] = o_idx;
+                    if (do_hist) {
+                        atomicAdd(&s_hist[(tile >> (digits.shift[0] - 32)) & digits.mask[0]], 1u);
+                        if (digits.num_passes > 1) {
+                            const uint32_t d1    = (tile >> (digits.shift[1] - 32)) & digits.mask[1];
+                            const unsigned peers = __match_any_sync(__activemask(), d1);
+                            if ((peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_hist[(1 << digits.radix_bits) + d1], (uint32_t)__popc(peers));
+                        }
+                    }
                 }
             }
+        }
+    }
+    if (do_hist) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
+            const uint32_t c = s_hist[k];
+            if (c) atomicAdd(digits.hist + k, c);
         }
     }
 }
@@ -164,19 +188,36 @@ __global__ void __launch_bounds__(256)
         n = *d_n;
         if (n > capacity) n = capacity;
     }
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-        const uint32_t cur = (uint32_t)(keys[k] >> 32);
+    // boundary between sorted positions k-1 and k (shad_get_ranges, shader.cpp:73-99)
+    auto boundary = [&](size_t k, uint32_t prev, uint32_t cur) {
         if (k == 0) {
             if (cur < num_tiles) ranges[2 * cur] = 0u;
-        } else {
-            const uint32_t prev = (uint32_t)(keys[k - 1] >> 32);
-            if (cur != prev) {
-                if (prev < num_tiles) ranges[2 * prev + 1] = (uint32_t)k;
-                if (cur < num_tiles) ranges[2 * cur] = (uint32_t)k;
-            }
+        } else if (cur != prev) {
+            if (prev < num_tiles) ranges[2 * prev + 1] = (uint32_t)k;
+            if (cur < num_tiles) ranges[2 * cur] = (uint32_t)k;
         }
         if (k == n - 1 && cur < num_tiles) ranges[2 * cur + 1] = (uint32_t)n;
+    };
+    // four keys per thread and iteration: two 16-byte loads plus the predecessor's tile id
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (size_t k = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; k < n; k += stride) {
+        if (k + 3 < n) {
+            const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(keys + k));
+            const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2*>(keys + k) + 1);
+            const uint32_t   t0 = (uint32_t)(a.x >> 32), t1 = (uint32_t)(a.y >> 32), t2 = (uint32_t)(b.x >> 32), t3 = (uint32_t)(b.y >> 32);
+            const uint32_t   tp = k ? (uint32_t)(__ldg(keys + k - 1) >> 32) : 0u;
+            boundary(k, tp, t0);
+            boundary(k + 1, t0, t1);
+            boundary(k + 2, t1, t2);
+            boundary(k + 3, t2, t3);
+        } else {
+            uint32_t prev = k ? (uint32_t)(__ldg(keys + k - 1) >> 32) : 0u;
+            for (size_t j = k; j < n; j++) {
+                const uint32_t cur = (uint32_t)(__ldg(keys + j) >> 32);
+                boundary(j, prev, cur);
+                prev = cur;
+            }
+        }
     }
 }
 
@@ -207,9 +248,14 @@ int launch_duplicate_keys(lcgs_b200_ctx* ctx, int P, int W, int H, const float* 
 
 int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, const uint32_t* order,
                                  const uint32_t* skeys, const uint2* rects, const uint32_t* offsets2, uint64_t* keys,
-                                 uint32_t* vals, size_t capacity, int row0, cudaStream_t s)
+                                 uint32_t* vals, size_t capacity, int row0, const SortDigits* digits, cudaStream_t s)
 {
     if (P <= 0) return LCGS_B200_OK;
+    // fused histograms need the digits to live in the tile id (key bits >= 32) and at most two passes
+    SortDigits dg{};
+    if (digits && digits->hist && digits->num_passes >= 1 && digits->num_passes <= 2 && digits->radix_bits <= 9 &&
+        digits->shift[0] >= 32)
+        dg = *digits;
     const uint32_t gx           = (uint32_t)((W + 15) / 16);
     const long     warps_needed = ((long)P + 31) / 32;
     long           blocks       = (warps_needed + 7) / 8;
@@ -217,7 +263,7 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
     if (blocks > max_blocks) blocks = max_blocks;
     duplicate_keys_sorted_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, order, skeys, rects,
                                                                  offsets2, reinterpret_cast<unsigned long long*>(keys), vals,
-                                                                 capacity);
+                                                                 capacity, dg);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }
@@ -229,7 +275,8 @@ int launch_ranges(lcgs_b200_ctx* ctx, const uint64_t* keys, size_t n_host, const
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), s));
     const size_t bound = d_n ? capacity : n_host;
     if (bound == 0) return LCGS_B200_OK;
-    size_t       blocks     = (bound + 1023) / 1024;
+    LCGS_REQUIRE(ctx, (((uintptr_t)keys) & 15) == 0, "tile_ranges: keys must be 16-byte aligned");
+    size_t       blocks     = (bound + 4095) / 4096;
     const size_t max_blocks = (size_t)ctx->num_sms * 8;
     if (blocks > max_blocks) blocks = max_blocks;
     tile_ranges_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(keys), n_host, d_n,

@@ -123,20 +123,26 @@ static int splat_tail(lcgs_b200_ctx* ctx, int P, const lcgs_b200_frame* fr, cons
     uint32_t* d_m = ctx->d_scalars + LCGS_SCALAR_NUM_TOUCHING;
     if (depth_ordered) {
         const OrderWs o = order_ws_views(ctx, P);
-        if ((rc = launch_scan_compact(ctx, fr->tiles_touched, fr->depth, P, fr->point_offsets, o.ckeys, o.cvals, d_n, d_m, s)))
+        SortDigits    dg32, dg64;
+        // depth >= 0.2 > 0: the sign bit is clear, 31 key bits.  The compaction kernel also fills the
+        // depth sort's digit histograms, the emission kernel those of the tile sort.
+        if ((rc = sort_prepare_u32(ctx, (size_t)P, 0, 31, &dg32, s))) return rc;
+        if ((rc = launch_scan_compact(ctx, fr->tiles_touched, fr->depth, P, fr->point_offsets, o.ckeys, o.cvals, d_n, d_m, &dg32, s)))
             return rc;
         mark(ctx, s);
-        // depth >= 0.2 > 0: the sign bit is clear, 31 key bits
-        if ((rc = launch_sort_u32(ctx, o.ckeys, o.skeys, o.cvals, o.svals, 0, d_m, (size_t)P, 0, 31, s))) return rc;
+        const bool hist32 = dg32.hist && dg32.num_passes <= 4;
+        if ((rc = sort_run_u32(ctx, o.ckeys, o.skeys, o.cvals, o.svals, d_m, (size_t)P, hist32, s))) return rc;
         if ((rc = launch_scan_gather(ctx, o.svals, o.rects, d_m, P, o.offsets2, s))) return rc;
         mark(ctx, s);
+        if ((rc = sort_prepare_u64(ctx, fr->list_capacity, 32, g.end_bit, &dg64, s))) return rc;
+        const bool hist64 = dg64.hist && dg64.num_passes >= 1 && dg64.num_passes <= 2;
         if ((rc = launch_duplicate_keys_sorted(ctx, d_m, P, g.W, o.svals, o.skeys, o.rects, o.offsets2,
                                                fr->point_list_keys_unsorted, fr->point_list_unsorted, fr->list_capacity,
-                                               g.row0, s)))
+                                               g.row0, hist64 ? &dg64 : nullptr, s)))
             return rc;
         mark(ctx, s);
-        if ((rc = launch_sort(ctx, fr->point_list_keys_unsorted, fr->point_list_keys, fr->point_list_unsorted,
-                              fr->point_list, 0, d_n, fr->list_capacity, 32, g.end_bit, s)))
+        if ((rc = sort_run_u64(ctx, fr->point_list_keys_unsorted, fr->point_list_keys, fr->point_list_unsorted,
+                               fr->point_list, d_n, fr->list_capacity, hist64, s)))
             return rc;
         mark(ctx, s);
     } else {
@@ -239,6 +245,7 @@ int lcgs_b200_ctx_destroy(lcgs_b200_ctx* ctx)
     if (ctx->sort_ws.ptr) cudaFree(ctx->sort_ws.ptr);
     if (ctx->record_ws.ptr) cudaFree(ctx->record_ws.ptr);
     if (ctx->order_ws.ptr) cudaFree(ctx->order_ws.ptr);
+    sort_free_plans(ctx);
     for (int i = 0; i < 16; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 3; i++)

@@ -57,6 +57,8 @@ struct lcgs_b200_ctx {
     cudaEvent_t  ev[16];
     int          ev_count   = 0;
     int          ev_valid   = 0;
+    void*        plan32 = nullptr;   // prepared sorts of the fused path (sort.cu)
+    void*        plan64 = nullptr;
     cudaEvent_t  ev_sort[3] = { nullptr, nullptr, nullptr };  // before histogram, before passes, after passes
     int          sort_passes = 0;
     int          ev_sort_valid = 0;
@@ -95,16 +97,29 @@ int ws_reserve(lcgs_b200_ctx* ctx, Workspace& ws, size_t bytes);
 // stage launchers (one group per .cu); all enqueue on `s` and return an lcgs_b200_status
 int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b200_view_params* vp,
                             const lcgs_b200_frame* fr, float4* records, uint2* rects, cudaStream_t s);
+struct SortDigits;
 int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const float* depth, int P, uint32_t* offsets,
-                        uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, cudaStream_t s);
+                        uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, const SortDigits* digits,
+                        cudaStream_t s);
 int launch_scan_gather(lcgs_b200_ctx* ctx, const uint32_t* order, const uint2* rects, const uint32_t* d_n, int capacity,
                        uint32_t* offsets2, cudaStream_t s);
 int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, const uint32_t* order,
                                  const uint32_t* skeys, const uint2* rects, const uint32_t* offsets2, uint64_t* keys,
-                                 uint32_t* vals, size_t capacity, int row0, cudaStream_t s);
-int launch_sort_u32(lcgs_b200_ctx* ctx, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
-                    uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
-                    cudaStream_t s);
+                                 uint32_t* vals, size_t capacity, int row0, const SortDigits* digits, cudaStream_t s);
+// digit layout of a prepared sort, for kernels that accumulate its histograms while producing the keys
+struct SortDigits {
+    uint32_t* hist;  // [num_passes][1 << radix_bits], zeroed
+    int       num_passes, radix_bits;
+    int       shift[kMaxSortPasses];
+    uint32_t  mask[kMaxSortPasses];
+};
+void sort_free_plans(lcgs_b200_ctx* ctx);
+int sort_prepare_u32(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s);
+int sort_run_u32(lcgs_b200_ctx* ctx, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                 const uint32_t* d_n, size_t capacity, bool hist_ready, cudaStream_t s);
+int sort_prepare_u64(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s);
+int sort_run_u64(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                 const uint32_t* d_n, size_t capacity, bool hist_ready, cudaStream_t s);
 int launch_sh(lcgs_b200_ctx* ctx, int P, int deg, const float* cam_pos, const float* pos, const float* sh, float* color,
               cudaStream_t s);
 int launch_project(lcgs_b200_ctx* ctx, int P, const float* pos, const float* scale, const float* rotq,

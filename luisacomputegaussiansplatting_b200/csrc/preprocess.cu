@@ -111,22 +111,22 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
     __syncthreads();
 
     // ---- phase 2: coalesced, predicated SH fetch into padded shared memory -------------------
+    // cp.async (LDGSTS) moves the 16-byte pieces global -> shared without passing through registers,
+    // so all 12 requests of a thread are in flight at once at no register cost.
     if (a.sh_deg == 3) {
-        const float4* src = reinterpret_cast<const float4*>(a.sh) + g0 * kShRowF4;
-        float4        v[kShRowF4];
-        int           dst[kShRowF4];
+        const float4*  src   = reinterpret_cast<const float4*>(a.sh) + g0 * kShRowF4;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_sh);
 #pragma unroll
         for (int j = 0; j < kShRowF4; j++) {
             const int idx = j * kPreThreads + t;
             const int g   = idx / kShRowF4;
             const int c   = idx - g * kShRowF4;
-            const bool on = s_need[g] != 0;  // implies g0 + g < P
-            dst[j]        = on ? g * kShRowPad + c : -1;
-            if (on) v[j] = __ldg(src + idx);
+            if (s_need[g] != 0)  // implies g0 + g < P
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)(g * kShRowPad + c) * 16u),
+                             "l"(src + idx)
+                             : "memory");
         }
-#pragma unroll
-        for (int j = 0; j < kShRowF4; j++)
-            if (dst[j] >= 0) s_sh[dst[j]] = v[j];
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 

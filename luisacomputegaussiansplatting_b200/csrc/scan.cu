@@ -180,8 +180,13 @@ __global__ void __launch_bounds__(kScanThreads)
     scan_compact_kernel(const uint32_t* __restrict__ tiles_touched, const float* __restrict__ depth, uint32_t n,
                         uint32_t num_tiles, uint32_t* __restrict__ offsets, uint32_t* __restrict__ ckeys,
                         uint32_t* __restrict__ cvals, unsigned long long* status_sum, unsigned long long* status_cnt,
-                        uint32_t* ticket, uint32_t* d_total, uint32_t* d_count)
+                        uint32_t* ticket, uint32_t* d_total, uint32_t* d_count, const __grid_constant__ SortDigits digits)
 {
+    // digit histograms of the depth keys this CTA compacts (the depth sort then skips its histogram kernel)
+    __shared__ uint32_t s_hist[4 * 512];
+    const bool          do_hist = digits.hist != nullptr;
+    const int           nbins   = do_hist ? (digits.num_passes << digits.radix_bits) : 0;
+    for (int k = threadIdx.x; k < nbins; k += kScanThreads) s_hist[k] = 0u;
     __shared__ uint32_t s_tile;
     __shared__ ScanPair s_warp[kScanThreads / 32];
     __shared__ uint32_t s_prefix[2];
@@ -223,9 +228,15 @@ __global__ void __launch_bounds__(kScanThreads)
         sum += v[k];
         out[k] = sum;
         if (v[k] > 0u) {  // stable compaction: slots are handed out in index order
-            ckeys[cnt] = __float_as_uint(__ldg(depth + e0 + k));
+            const uint32_t key = __float_as_uint(__ldg(depth + e0 + k));
+            ckeys[cnt] = key;
             cvals[cnt] = e0 + k;
             cnt++;
+            if (do_hist) {
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+                    if (p < digits.num_passes) atomicAdd(&s_hist[(p << digits.radix_bits) + ((key >> digits.shift[p]) & digits.mask[p])], 1u);
+            }
         }
     }
     if (e0 + kCompactItems <= n) {
@@ -235,6 +246,13 @@ __global__ void __launch_bounds__(kScanThreads)
 #pragma unroll
         for (int k = 0; k < kCompactItems; k++)
             if (e0 + k < n) offsets[e0 + k] = out[k];
+    }
+    if (do_hist) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < nbins; k += kScanThreads) {
+            const uint32_t c = s_hist[k];
+            if (c) atomicAdd(digits.hist + k, c);
+        }
     }
 }
 
@@ -288,8 +306,11 @@ __global__ void __launch_bounds__(kScanThreads)
 }
 
 int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const float* depth, int P, uint32_t* offsets,
-                        uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, cudaStream_t s)
+                        uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, const SortDigits* digits,
+                        cudaStream_t s)
 {
+    SortDigits dg{};
+    if (digits && digits->hist && digits->num_passes <= 4 && digits->radix_bits <= 9) dg = *digits;
     if (P <= 0) {
         LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint32_t), s));
         LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s));
@@ -304,7 +325,7 @@ int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
     auto* st = (unsigned long long*)ctx->scan_ws.ptr;
     scan_compact_kernel<<<tiles, kScanThreads, 0, s>>>(tiles_touched, depth, (uint32_t)P, tiles, offsets, ckeys, cvals, st,
-                                                       st + tiles, ticket, d_total, d_count);
+                                                       st + tiles, ticket, d_total, d_count, dg);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }

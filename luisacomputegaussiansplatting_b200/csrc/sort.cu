@@ -434,16 +434,20 @@ struct SweepTable<uint32_t> {
     static const char* env() { return "LCGS_SORT32_VARIANT"; }
 };
 
+// Geometry used for a sort over `bits` key bits: the environment override (tuning), else 7-bit digits
+// when two of them cover the range (the fused frame's 13 tile bits), else 9-bit digits.
 template <typename KeyT>
-static int sweep_variant_index()
+static int sweep_variant_index(int bits)
 {
-    static int idx = -1;
-    if (idx < 0) {
-        idx           = 0;
+    static int env_idx = -2;
+    if (env_idx == -2) {
+        env_idx       = -1;
         const char* e = getenv(SweepTable<KeyT>::env());
-        if (e && atoi(e) >= 0 && atoi(e) < SweepTable<KeyT>::count()) idx = atoi(e);
+        if (e && atoi(e) >= 0 && atoi(e) < SweepTable<KeyT>::count()) env_idx = atoi(e);
     }
-    return idx;
+    if (env_idx >= 0) return env_idx;
+    if (sizeof(KeyT) == 8 && bits <= 14) return 8;
+    return 0;
 }
 
 // workspace layout: [hist: passes*512 u32][status: passes*tiles*RADIX u32][tmp keys][tmp vals]
@@ -467,23 +471,31 @@ static size_t sort_ws_layout(size_t n, size_t key_bytes, size_t* off_status, siz
 
 size_t sort_temp_bytes(size_t n) { return sort_ws_layout(n, sizeof(uint64_t), nullptr, nullptr, nullptr); }
 
+// Everything launch_sort_t needs to know about one sort; filled by sort_prepare_t.
 template <typename KeyT>
-static int launch_sort_t(lcgs_b200_ctx* ctx, const KeyT* kin, KeyT* kout, const uint32_t* vals_in, uint32_t* vals_out,
-                         size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit, uint32_t* ticket,
-                         bool record_events, cudaStream_t s)
+struct SortPlan {
+    SortPassInfo info;
+    int          variant;
+    size_t       bound, tiles;
+    uint32_t *   hist, *status, *tmp_vals;
+    KeyT*        tmp_keys;
+};
+
+// Pass geometry + workspace + zeroed histograms / look-back status / tickets.  After this call another
+// kernel may accumulate the digit histograms itself (plan.hist, layout [pass][1 << radix_bits]) and
+// launch_sort_t can be told to skip its own histogram kernel.
+template <typename KeyT>
+static int sort_prepare_t(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, uint32_t* ticket, SortPlan<KeyT>* plan,
+                          cudaStream_t s)
 {
     constexpr int kKeyBits = (int)sizeof(KeyT) * 8;
     LCGS_REQUIRE(ctx, begin_bit >= 0 && end_bit <= kKeyBits && begin_bit <= end_bit, "sort: bad bit range");
-    const size_t bound = d_n ? capacity : n_host;  // upper bound on the number of pairs
-    if (bound == 0) return LCGS_B200_OK;
     LCGS_REQUIRE(ctx, bound <= (size_t)kStatusValueMask, "sort: more than 2^30-1 pairs");
-    if (!d_n) capacity = n_host;
-
-    const int                 vi    = sweep_variant_index<KeyT>();
-    const SweepVariant<KeyT>& var   = SweepTable<KeyT>::table()[vi];
     const int                 bits  = end_bit - begin_bit;
+    const int                 vi    = sweep_variant_index<KeyT>(bits);
+    const SweepVariant<KeyT>& var   = SweepTable<KeyT>::table()[vi];
     const int                 rbits = var.radix_bits;
-    SortPassInfo              info;
+    SortPassInfo&             info  = plan->info;
     info.radix_bits = rbits;
     info.num_passes = (bits + rbits - 1) / rbits;
     LCGS_REQUIRE(ctx, info.num_passes <= kMaxSortPasses, "sort: too many passes");
@@ -493,7 +505,36 @@ static int launch_sort_t(lcgs_b200_ctx* ctx, const KeyT* kin, KeyT* kout, const 
         info.shift[p] = lo < kKeyBits ? lo : 0;
         info.mask[p]  = w > 0 ? ((1u << w) - 1u) : 0u;
     }
+    plan->variant = vi;
+    plan->bound   = bound;
+    plan->tiles   = (bound + var.tile - 1) / var.tile;
+    plan->hist    = nullptr;
+    if (info.num_passes == 0 || bound == 0) return LCGS_B200_OK;
 
+    size_t       off_status, off_keys, off_vals;
+    const size_t bytes = sort_ws_layout(bound, sizeof(KeyT), &off_status, &off_keys, &off_vals);
+    int          rc    = ws_reserve(ctx, ctx->sort_ws, bytes);
+    if (rc) return rc;
+    char* ws       = (char*)ctx->sort_ws.ptr;
+    plan->hist     = (uint32_t*)ws;
+    plan->status   = (uint32_t*)(ws + off_status);
+    plan->tmp_keys = (KeyT*)(ws + off_keys);
+    plan->tmp_vals = (uint32_t*)(ws + off_vals);
+    // zero histograms + look-back status (contiguous) and the tickets
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ws, 0, off_status + (size_t)info.num_passes * plan->tiles * (1u << rbits) * sizeof(uint32_t), s));
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, kMaxSortPasses * sizeof(uint32_t), s));
+    return LCGS_B200_OK;
+}
+
+template <typename KeyT>
+static int launch_sort_t(lcgs_b200_ctx* ctx, const SortPlan<KeyT>& plan, const KeyT* kin, KeyT* kout, const uint32_t* vals_in,
+                         uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, uint32_t* ticket,
+                         bool hist_ready, bool record_events, cudaStream_t s)
+{
+    const size_t bound = plan.bound;
+    if (bound == 0) return LCGS_B200_OK;
+    const SortPassInfo&       info = plan.info;
+    const SweepVariant<KeyT>& var  = SweepTable<KeyT>::table()[plan.variant];
     const unsigned grid_stride_blocks = (unsigned)(((bound + 1023) / 1024) < (size_t)ctx->num_sms * 8
                                                        ? ((bound + 1023) / 1024)
                                                        : (size_t)ctx->num_sms * 8);
@@ -502,33 +543,21 @@ static int launch_sort_t(lcgs_b200_ctx* ctx, const KeyT* kin, KeyT* kout, const 
         LCGS_CUDA_CHECK(ctx, cudaGetLastError());
         return LCGS_B200_OK;
     }
-
-    size_t       off_status, off_keys, off_vals;
-    const size_t bytes = sort_ws_layout(bound, sizeof(KeyT), &off_status, &off_keys, &off_vals);
-    int          rc    = ws_reserve(ctx, ctx->sort_ws, bytes);
-    if (rc) return rc;
-    char*        ws       = (char*)ctx->sort_ws.ptr;
-    uint32_t*    hist     = (uint32_t*)ws;
-    uint32_t*    status   = (uint32_t*)(ws + off_status);
-    KeyT*        tmp_keys = (KeyT*)(ws + off_keys);
-    uint32_t*    tmp_vals = (uint32_t*)(ws + off_vals);
-    const int    radix    = 1 << rbits;
-    const size_t tiles    = (bound + var.tile - 1) / var.tile;
-
-    // zero histograms + look-back status (contiguous) and the tickets
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ws, 0, off_status + (size_t)info.num_passes * tiles * radix * sizeof(uint32_t), s));
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, kMaxSortPasses * sizeof(uint32_t), s));
+    const int    radix = 1 << info.radix_bits;
+    const size_t tiles = plan.tiles;
 
     const bool prof = record_events && ctx->profiling && ctx->ev_sort[0];
     if (prof) cudaEventRecord(ctx->ev_sort[0], s);
-    radix_histogram_kernel<KeyT><<<grid_stride_blocks, 256, 0, s>>>(kin, n_host, d_n, capacity, hist, info);
-    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    if (!hist_ready) {
+        radix_histogram_kernel<KeyT><<<grid_stride_blocks, 256, 0, s>>>(kin, n_host, d_n, capacity, plan.hist, info);
+        LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    }
     if (prof) cudaEventRecord(ctx->ev_sort[1], s);
 
     static bool smem_attr_set[16] = {};  // opt in to > 48 KB of dynamic shared memory once per process
-    if (!smem_attr_set[vi]) {
+    if (!smem_attr_set[plan.variant]) {
         LCGS_CUDA_CHECK(ctx, cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
-        smem_attr_set[vi] = true;
+        smem_attr_set[plan.variant] = true;
     }
     const size_t   max_ctas     = (size_t)ctx->num_sms * var.blocks_per_sm;
     const unsigned sweep_blocks = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
@@ -556,11 +585,12 @@ static int launch_sort_t(lcgs_b200_ctx* ctx, const KeyT* kin, KeyT* kout, const 
     const uint32_t* src_v = vals_in;
     for (int p = 0; p < info.num_passes; p++) {
         const bool to_out = ((info.num_passes - 1 - p) % 2) == 0;
-        KeyT*      dst_k  = to_out ? kout : tmp_keys;
-        uint32_t*  dst_v  = to_out ? vals_out : tmp_vals;
+        KeyT*      dst_k  = to_out ? kout : plan.tmp_keys;
+        uint32_t*  dst_v  = to_out ? vals_out : plan.tmp_vals;
         var.kernel<<<sweep_blocks, var.threads, var.smem, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
-                                                              hist + (size_t)p * radix, status + (size_t)p * tiles * radix,
-                                                              ticket + p, info.shift[p], info.mask[p], dbg);
+                                                              plan.hist + (size_t)p * radix,
+                                                              plan.status + (size_t)p * tiles * radix, ticket + p,
+                                                              info.shift[p], info.mask[p], dbg);
         LCGS_CUDA_CHECK(ctx, cudaGetLastError());
         src_k = dst_k;
         src_v = dst_v;
@@ -577,18 +607,65 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
                 uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
                 cudaStream_t s)
 {
-    return launch_sort_t<unsigned long long>(ctx, reinterpret_cast<const unsigned long long*>(keys_in),
+    const size_t bound = d_n ? capacity : n_host;
+    if (bound == 0) return LCGS_B200_OK;
+    if (!d_n) capacity = n_host;
+    uint32_t*                    ticket = ctx->d_scalars + LCGS_SCALAR_SORT_TICKET;
+    SortPlan<unsigned long long> plan;
+    int rc = sort_prepare_t<unsigned long long>(ctx, bound, begin_bit, end_bit, ticket, &plan, s);
+    if (rc) return rc;
+    return launch_sort_t<unsigned long long>(ctx, plan, reinterpret_cast<const unsigned long long*>(keys_in),
                                              reinterpret_cast<unsigned long long*>(keys_out), vals_in, vals_out, n_host, d_n,
-                                             capacity, begin_bit, end_bit, ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, true, s);
+                                             capacity, ticket, false, true, s);
 }
 
-// per-Gaussian (depth bits, index) sort of the fused path; shares the context's sort workspace
-int launch_sort_u32(lcgs_b200_ctx* ctx, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
-                    uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
-                    cudaStream_t s)
+// ---- fused path: the kernel that PRODUCES the keys also accumulates the digit histograms ------------
+// sort_prepare_* zeroes the workspace and returns where the histograms live and how digits are cut;
+// sort_run_* then launches only the onesweep passes.
+int sort_prepare_u32(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s)
 {
-    return launch_sort_t<uint32_t>(ctx, keys_in, keys_out, vals_in, vals_out, n_host, d_n, capacity, begin_bit, end_bit,
-                                   ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, false, s);
+    if (!ctx->plan32) ctx->plan32 = new SortPlan<uint32_t>();
+    auto& plan = *static_cast<SortPlan<uint32_t>*>(ctx->plan32);
+    int   rc   = sort_prepare_t<uint32_t>(ctx, bound, begin_bit, end_bit, ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, &plan, s);
+    if (rc) return rc;
+    digits->hist = plan.hist; digits->num_passes = plan.info.num_passes; digits->radix_bits = plan.info.radix_bits;
+    for (int p = 0; p < kMaxSortPasses; p++) { digits->shift[p] = plan.info.shift[p]; digits->mask[p] = plan.info.mask[p]; }
+    return LCGS_B200_OK;
+}
+
+int sort_run_u32(lcgs_b200_ctx* ctx, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                 const uint32_t* d_n, size_t capacity, bool hist_ready, cudaStream_t s)
+{
+    const auto& plan = *static_cast<const SortPlan<uint32_t>*>(ctx->plan32);
+    return launch_sort_t<uint32_t>(ctx, plan, keys_in, keys_out, vals_in, vals_out, 0, d_n, capacity,
+                                   ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, hist_ready, false, s);
+}
+
+int sort_prepare_u64(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s)
+{
+    if (!ctx->plan64) ctx->plan64 = new SortPlan<unsigned long long>();
+    auto& plan = *static_cast<SortPlan<unsigned long long>*>(ctx->plan64);
+    int   rc   = sort_prepare_t<unsigned long long>(ctx, bound, begin_bit, end_bit, ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, &plan, s);
+    if (rc) return rc;
+    digits->hist = plan.hist; digits->num_passes = plan.info.num_passes; digits->radix_bits = plan.info.radix_bits;
+    for (int p = 0; p < kMaxSortPasses; p++) { digits->shift[p] = plan.info.shift[p]; digits->mask[p] = plan.info.mask[p]; }
+    return LCGS_B200_OK;
+}
+
+int sort_run_u64(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                 const uint32_t* d_n, size_t capacity, bool hist_ready, cudaStream_t s)
+{
+    const auto& plan = *static_cast<const SortPlan<unsigned long long>*>(ctx->plan64);
+    return launch_sort_t<unsigned long long>(ctx, plan, reinterpret_cast<const unsigned long long*>(keys_in),
+                                             reinterpret_cast<unsigned long long*>(keys_out), vals_in, vals_out, 0, d_n, capacity,
+                                             ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, hist_ready, true, s);
+}
+
+void sort_free_plans(lcgs_b200_ctx* ctx)
+{
+    delete static_cast<SortPlan<uint32_t>*>(ctx->plan32);
+    delete static_cast<SortPlan<unsigned long long>*>(ctx->plan64);
+    ctx->plan32 = ctx->plan64 = nullptr;
 }
 
 }  // namespace lcgs_b200

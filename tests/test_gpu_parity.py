@@ -294,3 +294,30 @@ def test_buffer_filler(lcgs, dev):
     c = torch.zeros(7, dtype=torch.float32, device="cuda")
     bf.fill(dev, a, 7), bf.fill(dev, b, 1 << 40), bf.fill(dev, c, 0.5)
     assert bool((a == 7).all()) and bool((b == (1 << 40)).all()) and bool((c == 0.5).all())
+
+
+def test_frame_is_capturable_in_a_cuda_graph(lcgs, dev):
+    """No allocation and no synchronisation inside lcgs_b200_render: the frame replays from a CUDA graph
+     and gives the same bits as the eager call."""
+    import torch
+    W, H, P = 400, 240, 12_000
+    sc, pose = make_case("C3", P, W, H)
+    vp = lcgs.view_params(lcgs.make_camera(*pose, W, H))
+    r = lcgs.Renderer(dev, sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, W, H, list_capacity=200_000)
+    r.render_async(vp)                      # warm-up: workspace reservation and function attributes
+    n = dev.num_rendered()
+    eager = r.intermediates(n)
+    r.img.zero_(), r.keys.zero_(), r.vals.zero_(), r.ranges.zero_()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            r.render_async(vp, stream=s)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    replay = r.intermediates(n)
+    for k in ("keys_sorted", "vals_sorted", "ranges", "tiles_touched", "radii"):
+        assert np.array_equal(eager[k], replay[k]), k
+    assert np.array_equal(bits(eager["img"]), bits(replay["img"]))
