@@ -24,6 +24,8 @@
 //
 // Compute-bound (FP32 issue + shared memory), not HBM-bound; HBM side is 4 B id + 48 B record per
 // instance (mostly L2 hits) + 12 B per pixel.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lcgs_b200 {
@@ -50,7 +52,8 @@ __device__ __forceinline__ float ex2_ftz(float x)
     return y;
 }
 
-__global__ void __launch_bounds__(kBlendThreads, 5)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
     blend_kernel(int W, int H, uint32_t gx, uint32_t row0, float bg0, float bg1, float bg2,
                  const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                  const float4* __restrict__ records, const uint32_t* __restrict__ d_num_rendered,
@@ -187,9 +190,17 @@ int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32
     if (row1 < 0) row1 = (int)gy;
     if (W <= 0 || H <= 0 || row1 <= row0) return LCGS_B200_OK;
     dim3 grid(gx, (unsigned)(row1 - row0));
-    blend_kernel<<<grid, kBlendThreads, 0, s>>>(W, H, gx, (uint32_t)row0, bg[0], bg[1], bg[2],
-                                                reinterpret_cast<const uint2*>(ranges), point_list, records,
-                                                d_num_rendered, img);
+    static int occ = -1;  // LCGS_BLEND_OCC: register budget as "CTAs per SM" (tuning only)
+    if (occ < 0) {
+        const char* e = getenv("LCGS_BLEND_OCC");
+        occ           = e ? atoi(e) : 5;
+    }
+    auto kern = blend_kernel<5>;
+    if (occ == 4) kern = blend_kernel<4>;
+    if (occ == 6) kern = blend_kernel<6>;
+    if (occ == 8) kern = blend_kernel<8>;
+    kern<<<grid, kBlendThreads, 0, s>>>(W, H, gx, (uint32_t)row0, bg[0], bg[1], bg[2], reinterpret_cast<const uint2*>(ranges),
+                                        point_list, records, d_num_rendered, img);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }
