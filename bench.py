@@ -48,12 +48,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3"])
+    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C5"])
     ap.add_argument("--gaussians", type=int, default=None, help="override P (debugging only; invalidates the number)")
     ap.add_argument("--orbit", action="store_true", help="rank r / step s renders orbit view s*N+r instead of the fixed pose")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--capacity", type=int, default=20_000_000, help="instance list capacity L (app/main.cpp:245)")
-    return ap.parse_args()
+    ap.add_argument("--capacity", type=int, default=None,
+                    help="instance list capacity L (default 20 000 000 = app/main.cpp:245; 260 000 000 for C5)")
+    args = ap.parse_args()
+    if args.capacity is None:
+        args.capacity = 260_000_000 if args.config == "C5" else 20_000_000
+    return args
 
 
 def peaks():
