@@ -94,7 +94,8 @@ typedef struct lcgs_b200_frame {
     int   width, height;
     float bg_color[3];
     /* GSTileSplatterInputProxy */
-    float* means_2d; /* [P][2] NDC after project, pixels after allocate_tiles (in-place, Q7); 8-byte aligned */
+    float* means_2d; /* [P][2] NDC after project, pixels after allocate_tiles (in-place, Q7); 8-byte aligned;
+                        optional in lcgs_b200_render */
     float* depth;    /* [P] */
     float* conic;    /* [P][3] optional; cov2d after project, conic after allocate_tiles (in-place) */
     float* color;    /* [P][3] optional */

@@ -82,7 +82,6 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
     const bool  inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;  // no half-pixel offset (Q2)
     const float tx0 = (float)tile_x0, ty0 = (float)tile_y0, tx1 = (float)(tile_x0 + 15), ty1 = (float)(tile_y0 + 15);
-    const float wx0 = (float)patch_x0, wy0 = (float)patch_y0, wx1 = (float)(patch_x0 + 7), wy1 = (float)(patch_y0 + 3);
 
     const uint32_t tile  = blockIdx.x + blockIdx.y * gx;
     const uint2    range = __ldg(ranges + tile);
@@ -134,6 +133,14 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
         // ---- consume round r: per segment, cull against the patch, evaluate the hits ----------------
         if (!__all_sync(FULL, done)) {
             const uint32_t abase = sbase + buf * kBuf;
+            // the patch shrinks to the bounding box of the pixels that are still accumulating: saturated
+            // pixels need no more Gaussians, so later rounds cull against a smaller rectangle
+            const unsigned ax = done ? 255u : (unsigned)(lane & 7), ay = done ? 255u : (unsigned)(lane >> 3);
+            const unsigned bx = done ? 0u : (unsigned)(lane & 7), by = done ? 0u : (unsigned)(lane >> 3);
+            const float wx0 = (float)(patch_x0 + (int)__reduce_min_sync(FULL, ax));
+            const float wy0 = (float)(patch_y0 + (int)__reduce_min_sync(FULL, ay));
+            const float wx1 = (float)(patch_x0 + (int)__reduce_max_sync(FULL, bx));
+            const float wy1 = (float)(patch_y0 + (int)__reduce_max_sync(FULL, by));
 #pragma unroll 1
             for (int seg = 0; seg < kBlendWarps; seg++) {
                 const uint32_t cnt = s_cnt[buf][seg];

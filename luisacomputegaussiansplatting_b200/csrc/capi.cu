@@ -511,7 +511,7 @@ int lcgs_b200_render(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b
     LCGS_REQUIRE(ctx, P >= 0 && sc->sh_deg >= 0 && sc->sh_deg <= 3, "render: bad scene");
     LCGS_REQUIRE(ctx, P == 0 || (sc->pos && sc->scale && sc->rotq && sc->sh && sc->opacity), "render: null scene array");
     LCGS_REQUIRE(ctx, aligned(sc->rotq, 16) && aligned(sc->sh, 16), "render: rotq and sh must be 16-byte aligned");
-    LCGS_REQUIRE(ctx, fr->means_2d && aligned(fr->means_2d, 8), "render: means_2d is required (8-byte aligned)");
+    LCGS_REQUIRE(ctx, aligned(fr->means_2d, 8), "render: means_2d must be 8-byte aligned");
     LCGS_REQUIRE(ctx, vp->width == fr->width && vp->height == fr->height, "render: view/frame resolution mismatch");
     if ((rc = reserve_all(ctx, P > 0 ? P : 1, fr->list_capacity))) return rc;
     cudaStream_t s = as_stream(stream);

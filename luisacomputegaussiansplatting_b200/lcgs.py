@@ -371,7 +371,7 @@ class Renderer:
         self.capacity = int(list_capacity)
         z = lambda n, dt: torch.zeros(int(n), dtype=dt, device=dev)  # noqa: E731
         # main.cpp:232-254: the 12 frame buffers
-        self.means_2d = z(2 * P, torch.float32)
+        self.means_2d = z(2 * P, torch.float32) if keep_intermediates else None
         self.depth = z(P, torch.float32)
         self.conic = z(3 * P, torch.float32) if keep_intermediates else None
         self.color = z(3 * P, torch.float32) if keep_intermediates else None
@@ -439,12 +439,13 @@ class Renderer:
         n = self.device.num_rendered() if n is None else n
         u32 = lambda t: t.cpu().numpy().view(np.uint32)  # noqa: E731
         out = dict(
-            num_rendered=n, depth=self.depth.cpu().numpy(), means_2d=self.means_2d.cpu().numpy().reshape(-1, 2),
+            num_rendered=n, depth=self.depth.cpu().numpy(),
             tiles_touched=u32(self.tiles_touched), radii=self.radii.cpu().numpy(), offsets=u32(self.point_offsets),
             keys_unsorted=self.keys_unsorted[:n].cpu().numpy().view(np.uint64), vals_unsorted=u32(self.vals_unsorted[:n]),
             keys_sorted=self.keys[:n].cpu().numpy().view(np.uint64), vals_sorted=u32(self.vals[:n]),
             ranges=u32(self.ranges).reshape(-1, 2)[:self.num_tiles], img=self.image().cpu().numpy())
         if self.conic is not None:
+            out["means_2d"] = self.means_2d.cpu().numpy().reshape(-1, 2)
             out["conic"] = self.conic.cpu().numpy().reshape(-1, 3)
             out["color"] = self.color.cpu().numpy().reshape(-1, 3)
         return out

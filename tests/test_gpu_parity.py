@@ -321,3 +321,43 @@ def test_frame_is_capturable_in_a_cuda_graph(lcgs, dev):
     for k in ("keys_sorted", "vals_sorted", "ranges", "tiles_touched", "radii"):
         assert np.array_equal(eager[k], replay[k]), k
     assert np.array_equal(bits(eager["img"]), bits(replay["img"]))
+
+
+def _render_and_compare(lcgs, dev, sc, pose, W, H, sh=None, sh_deg=3, scale_modifier=1.0, bg=(0.0, 0.0, 0.0), opacity=None):
+    sh = sc.sh if sh is None else sh
+    opacity = sc.opacity if opacity is None else opacity
+    ovp = orc.view_params(orc.make_camera(*pose, W, H))
+    fr = orc.forward(sc.pos, sc.scale, sc.rotq, sh, opacity, ovp, bg=bg, sh_deg=sh_deg, scale_modifier=scale_modifier)
+    r = lcgs.Renderer(dev, sc.pos, sc.scale, sc.rotq, sh, opacity, W, H, list_capacity=max(fr.num_rendered, 1) + 5,
+                      sh_deg=sh_deg, scale_modifier=scale_modifier, bg_color=bg)
+    n = r.render(lcgs.make_camera(*pose, W, H))
+    assert_frame_matches(r.intermediates(n), fr, fused=True)
+    return fr
+
+
+def test_heavy_tailed_tiles_and_huge_splats(lcgs, dev):
+    """scale_modifier 25: Gaussians cover hundreds of tiles each (the warp-cooperative key emission and
+    long, saturating tile lists), non-black background."""
+    sc, pose = make_case("C3", 2500, 640, 360)
+    fr = _render_and_compare(lcgs, dev, sc, pose, 640, 360, scale_modifier=25.0, bg=(0.2, 0.4, 0.6))
+    assert fr.tiles_touched.max() > 300 and fr.num_rendered > 100_000
+    lens = fr.ranges[:, 1].astype(np.int64) - fr.ranges[:, 0]
+    assert lens.max() > 500
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2])
+def test_fused_render_with_lower_sh_degree(lcgs, dev, deg):
+    sc, pose = make_case("C3", 6000, 256, 160)
+    sh = np.ascontiguousarray(sc.sh[:, :(deg + 1) ** 2, :])
+    _render_and_compare(lcgs, dev, sc, pose, 256, 160, sh=sh, sh_deg=deg)
+
+
+def test_opacity_extremes(lcgs, dev):
+    """opacity 0, below 1/255 (never contributes: threshold +inf), exactly 1/255, and 1."""
+    sc, pose = make_case("C3", 8000, 320, 200)
+    op = sc.opacity.copy()
+    op[0::5] = 0.0
+    op[1::5] = 0.0039
+    op[2::5] = np.float32(1.0) / np.float32(255.0)
+    op[3::5] = 1.0
+    _render_and_compare(lcgs, dev, sc, pose, 320, 200, opacity=op, scale_modifier=3.0)
