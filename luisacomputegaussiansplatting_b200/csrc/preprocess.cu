@@ -59,12 +59,15 @@ __device__ __forceinline__ void write_record(float4* rec, const Splat2D& s, floa
 
 __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __grid_constant__ PreprocessArgs a)
 {
-    __shared__ float4  s_sh[kPreThreads * kShRowPad];
-    __shared__ uint8_t s_need[kPreThreads];
+    // Every warp works on its own 32 Gaussians and its own slice of shared memory: no block-wide
+    // barrier, so a warp waiting for its SH rows never holds up the others.
+    __shared__ float4 s_sh[kPreThreads * kShRowPad];
 
-    const int  t  = threadIdx.x;
-    const long g0 = (long)blockIdx.x * kPreThreads;
-    const long i  = g0 + t;
+    const int      t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const long     w0   = (long)blockIdx.x * kPreThreads + warp * 32;  // first Gaussian of this warp
+    const long     i    = w0 + lane;
+    float4* const  w_sh = s_sh + warp * 32 * kShRowPad;
 
     // ---- phase 1: geometry ----------------------------------------------------------------
     float   px = 0.f, py = 0.f, pz = 0.f;
@@ -107,28 +110,29 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
             }
         }
     }
-    s_need[t] = need ? 1 : 0;
-    __syncthreads();
+    const unsigned need_mask = __ballot_sync(FULL, need);
+    if (need_mask == 0u) return;
 
     // ---- phase 2: coalesced, predicated SH fetch into padded shared memory -------------------
-    // cp.async (LDGSTS) moves the 16-byte pieces global -> shared without passing through registers,
-    // so all 12 requests of a thread are in flight at once at no register cost.
+    // The warp's 32 rows are one contiguous 6 KB run; lane l copies 16-byte pieces l, l+32, ... of it
+    // with cp.async (LDGSTS: no register staging, all 12 requests of a lane in flight at once), but
+    // only the pieces of rows whose Gaussian touches a tile.
     if (a.sh_deg == 3) {
-        const float4*  src   = reinterpret_cast<const float4*>(a.sh) + g0 * kShRowF4;
-        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_sh);
+        const float4*  src   = reinterpret_cast<const float4*>(a.sh) + w0 * kShRowF4;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(w_sh);
 #pragma unroll
         for (int j = 0; j < kShRowF4; j++) {
-            const int idx = j * kPreThreads + t;
+            const int idx = j * 32 + lane;
             const int g   = idx / kShRowF4;
             const int c   = idx - g * kShRowF4;
-            if (s_need[g] != 0)  // implies g0 + g < P
+            if ((need_mask >> g) & 1u)  // implies w0 + g < P
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)(g * kShRowPad + c) * 16u),
                              "l"(src + idx)
                              : "memory");
         }
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
     }
-    __syncthreads();
 
     // ---- phase 3: colour + blend record ------------------------------------------------------
     if (need) {
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
             float r[48];
 #pragma unroll
             for (int k = 0; k < kShRowF4; k++) {
-                const float4 q = s_sh[t * kShRowPad + k];
+                const float4 q = w_sh[lane * kShRowPad + k];
                 r[4 * k] = q.x; r[4 * k + 1] = q.y; r[4 * k + 2] = q.z; r[4 * k + 3] = q.w;
             }
             sh_color(3, a.vp.cam_pos, px, py, pz, RegSh{ r }, rgb);
