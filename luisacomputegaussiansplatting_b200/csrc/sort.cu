@@ -408,6 +408,9 @@ static const SweepVariant<unsigned long long> kSweep64[] = {
     LCGS_SWEEP(unsigned long long, 256, 16, 7, 3, true),  // 9
     LCGS_SWEEP(unsigned long long, 256, 16, 7, 2, true),  // 10
     LCGS_SWEEP(unsigned long long, 512, 12, 7, 1, true),  // 11
+    LCGS_SWEEP(unsigned long long, 1024, 12, 7, 1, true), // 12: one 12288-pair tile per SM
+    LCGS_SWEEP(unsigned long long, 1024, 16, 7, 1, true), // 13: one 16384-pair tile per SM
+    LCGS_SWEEP(unsigned long long, 1024, 8, 7, 1, true),  // 14
 };
 // 32-bit depth keys of the per-Gaussian sort
 static const SweepVariant<uint32_t> kSweep32[] = {
@@ -554,10 +557,11 @@ static int launch_sort_t(lcgs_b200_ctx* ctx, const SortPlan<KeyT>& plan, const K
     }
     if (prof) cudaEventRecord(ctx->ev_sort[1], s);
 
-    static bool smem_attr_set[16] = {};  // opt in to > 48 KB of dynamic shared memory once per process
-    if (!smem_attr_set[plan.variant]) {
+    // opt in to > 48 KB of dynamic shared memory, once per context (function attributes are per device)
+    bool& attr_set = ctx->sweep_attr_set[sizeof(KeyT) == 8 ? 1 : 0][plan.variant];
+    if (!attr_set) {
         LCGS_CUDA_CHECK(ctx, cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
-        smem_attr_set[plan.variant] = true;
+        attr_set = true;
     }
     const size_t   max_ctas     = (size_t)ctx->num_sms * var.blocks_per_sm;
     const unsigned sweep_blocks = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
