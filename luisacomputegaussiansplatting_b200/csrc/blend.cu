@@ -5,15 +5,16 @@
 // list is consumed in rounds of 256 candidates through a double-buffered shared-memory stage:
 //   produce (round r+1): every thread gathers one Gaussian's packed 48-byte record (pixel mean,
 //      pre-scaled conic, alpha-test threshold, opacity, colour), tests it against the TILE
-//      rectangle with cull_rect(), and each warp compacts its survivors, order preserved, into its
+//      rectangle with cull_rect_fast(), and each warp compacts its survivors, order preserved, into its
 //      own 32-slot segment (ballot + popc; no block-wide prefix, no extra barrier);
 //   consume (round r): each warp walks the 8 segments; per segment one lane per survivor tests it
 //      against the warp's 8x4 PATCH, and only the ballot's set bits are evaluated, all 32 pixels on
 //      the same Gaussian with broadcast LDS.128.
 // The global gathers of round r+1 are in flight while round r is blended, and there is ONE
 // __syncthreads per round (it also carries the block-wide "every pixel saturated" vote).
-// cull_rect() (lcgs_math.cuh) is conservative with respect to the per-pixel float evaluation, so
-// culling only removes pairs the alpha test would have skipped: on the C3 scene 42 % of the
+// cull_rect_fast() (lcgs_math.cuh; branch-free, its two divisions precomputed per Gaussian in the
+// record) is conservative with respect to the per-pixel float evaluation, so culling only removes
+// pairs the alpha test would have skipped: on the C3 scene 42 % of the
 // (Gaussian, tile) instances binned by the reference's loose rect never touch their tile and 78 %
 // of the (Gaussian, patch) pairs are empty -- the reference evaluates all of them for 256 pixels.
 // Other differences that do not change results: colour is staged with the batch instead of fetched
@@ -37,6 +38,13 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
 {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ float lds32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
 
@@ -64,7 +72,7 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
     if (d_num_rendered && *d_num_rendered == 0u) return;
 
     // [buffer][plane][slot]: plane 0 = (pix.x, pix.y, -0.5*conic.x, -conic.y),
-    // plane 1 = (-0.5*conic.z, threshold, opacity, -), plane 2 = (r, g, b, -)
+    // plane 1 = (-0.5*conic.z, threshold, opacity, ry), plane 2 = (r, g, b, rx)
     __shared__ float4   s_rec[2][3][kBlendThreads];
     __shared__ uint32_t s_cnt[2][kBlendWarps];
 
@@ -88,12 +96,13 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
     const uint32_t len   = range.y > range.x ? range.y - range.x : 0u;
     const uint32_t nrounds = (len + kBlendThreads - 1) / kBlendThreads;
 
-    float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
-    bool  done = !inside;
+    // T < 0 marks a finished pixel (saturated, or outside the image); |T| is its final transmittance.
+    // A finished pixel needs no flag in the inner loop: T * (1 - alpha) is negative, so it never blends.
+    float T = inside ? 1.0f : -1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
 
     // cull one gathered candidate against the tile and append it to this warp's segment of `buf`
     auto produce = [&](uint32_t buf, bool valid, const float4& a, const float4& b, const float4& c) {
-        const bool     keep = valid && !cull_rect(a.x, a.y, a.z, a.w, b.x, b.y, tx0, ty0, tx1, ty1);
+        const bool     keep = valid && !cull_rect_fast(a.x, a.y, a.z, a.w, b.x, b.y, b.w, c.w, tx0, ty0, tx1, ty1);
         const unsigned kept = __ballot_sync(FULL, keep);
         if (keep) {
             const uint32_t slot = warp * 32 + __popc(kept & lt_mask);
@@ -131,6 +140,7 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
         if (nidx + kBlendThreads < len) next_id = __ldg(point_list + range.x + nidx + kBlendThreads);
 
         // ---- consume round r: per segment, cull against the patch, evaluate the hits ----------------
+        bool done = T < 0.0f;
         if (!__all_sync(FULL, done)) {
             const uint32_t abase = sbase + buf * kBuf;
             // the patch shrinks to the bounding box of the pixels that are still accumulating: saturated
@@ -143,34 +153,37 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
             const float wy1 = (float)(patch_y0 + (int)__reduce_max_sync(FULL, by));
 #pragma unroll 1
             for (int seg = 0; seg < kBlendWarps; seg++) {
-                const uint32_t cnt = s_cnt[buf][seg];
-                bool           hit = false;
+                const uint32_t cnt     = s_cnt[buf][seg];
+                const uint32_t segbase = abase + seg * 512u;
+                bool           hit     = false;
                 if ((uint32_t)lane < cnt) {
-                    const float4 ga = lds128(abase + (seg * 32 + lane) * 16u);
-                    const float4 gb = lds128(abase + kPlane + (seg * 32 + lane) * 16u);
-                    hit             = !cull_rect(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, wx0, wy0, wx1, wy1);
+                    const float4 ga = lds128(segbase + lane * 16u);
+                    const float4 gb = lds128(segbase + kPlane + lane * 16u);
+                    const float  rx = lds32(segbase + 2u * kPlane + lane * 16u + 12u);
+                    hit             = !cull_rect_fast(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.w, rx, wx0, wy0, wx1, wy1);
                 }
                 unsigned hits = __ballot_sync(FULL, hit);
                 while (hits) {
-                    const uint32_t addr = abase + (seg * 32 + __ffs(hits) - 1) * 16u;
+                    const uint32_t addr = segbase + (__ffs(hits) - 1) * 16u;
                     hits &= hits - 1u;
                     const float4 ea = lds128(addr);
                     const float4 eb = lds128(addr + kPlane);
                     const float4 ec = lds128(addr + 2u * kPlane);
                     // canonical evaluation (shared with the oracle), two explicit fused ops
                     const float power = blend_power(ea.z, ea.w, eb.x, ea.x - pxf, ea.y - pyf);
-                    // shader.cpp:257,259: skipped pairs (and saturated pixels) are predicated off
-                    const bool  ok     = !done && !(power > 0.0f) && !(power < eb.y);
+                    // shader.cpp:257,259: skipped pairs are predicated off
+                    const bool  ok     = !(power > 0.0f) && !(power < eb.y);
                     const float alpha  = fminf(0.99f, eb.z * ex2_ftz(power * 1.4426950408889634f));
-                    const float test_T = T * (1.0f - alpha);
+                    const float test_T = T * (1.0f - alpha);         // < 0 for a finished pixel
                     const bool  blend  = ok && !(test_T < 0.0001f);  // shader.cpp:261-265
-                    done               = done || (ok && !blend);     // saturated: this entry is not blended
                     const float w      = blend ? T * alpha : 0.0f;
                     C0 = __fmaf_rn(w, ec.x, C0);
                     C1 = __fmaf_rn(w, ec.y, C1);
                     C2 = __fmaf_rn(w, ec.z, C2);
-                    T  = blend ? test_T : T;
+                    // saturated (ok but not blended): this entry is dropped and the pixel is finished
+                    T = ok ? (blend ? test_T : -fabsf(T)) : T;
                 }
+                done = T < 0.0f;
                 if (__all_sync(FULL, done)) break;
             }
         }
@@ -178,12 +191,13 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
         // ---- produce round r+1 into the other buffer ------------------------------------------------
         if (r + 1u < nrounds) produce(buf ^ 1u, next_valid, ra, rb, rc);
         // one barrier per round: publishes buffer buf^1, retires buffer buf, votes on early exit
-        if (__syncthreads_and(done)) break;
+        if (__syncthreads_and(T < 0.0f)) break;
     }
 
     if (inside) {
         const size_t plane = (size_t)W * (size_t)H;
         const size_t pix   = (size_t)px + (size_t)W * (size_t)py;
+        T                    = fabsf(T);
         img[pix]             = __fmaf_rn(bg0, T, C0);
         img[pix + plane]     = __fmaf_rn(bg1, T, C1);
         img[pix + 2 * plane] = __fmaf_rn(bg2, T, C2);

@@ -439,4 +439,66 @@ LCGS_HD bool cull_rect(float mx, float my, float a, float b, float c, float thr,
     return pmax + margin < thr;
 }
 
+// ---------------------------------------------------------------------------------------------
+// cull_rect() with the two divisions hoisted out: the blend kernel tests every Gaussian of a tile
+// against the tile and then against each warp's patch, so the per-Gaussian quotients
+//   ry = -b / (2c)   (dy of the maximiser per unit dx along a vertical edge)
+//   rx = -b / (2a)   (dx of the maximiser per unit dy along a horizontal edge)
+// are computed once in the preprocess and travel in the two spare record slots.  ry = NaN marks a
+// Gaussian that must never be culled (non-concave form, non-finite mean/conic, NaN threshold);
+// cull_rect_fast() is branch-free otherwise:
+//   xe, ye   the offset of smallest magnitude inside [dxl,dxh] / [dyl,dyh] (0 when the mean's
+//            column / row crosses the rectangle);
+//   p1, p2   the form on the vertical / horizontal line through xe / ye at the clamped maximiser.
+// Both points lie inside the rectangle and one of them is the exact maximiser (cull_rect()'s
+// argument; when the mean is inside both are 0), so max(p1,p2) + margin bounds every per-pixel
+// evaluation from above.  The margin is the same as cull_rect()'s.
+// ---------------------------------------------------------------------------------------------
+struct CullCoef {
+    float ry, rx;
+};
+
+LCGS_HD float cull_fma(float x, float y, float z)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(x, y, z);
+#else
+    return fmaf(x, y, z);
+#endif
+}
+
+LCGS_HD CullCoef cull_coef(float mx, float my, float a, float b, float c, float thr)
+{
+    CullCoef k;
+    const float big = 1.0e30f;
+    const bool  concave = a < 0.0f && c < 0.0f && a > -big && c > -big && 4.0f * a * c - b * b > 0.0f;
+    const bool  finite  = fabsf(mx) < big && fabsf(my) < big;
+    const bool  thr_ok  = thr <= 0.0f || thr > 0.0f;  // not NaN
+    if (concave && finite && thr_ok) {
+        k.ry = -b / (2.0f * c);
+        k.rx = -b / (2.0f * a);
+    } else {
+        k.ry = NAN;
+        k.rx = 0.0f;
+    }
+    return k;
+}
+
+LCGS_HD bool cull_rect_fast(float mx, float my, float a, float b, float c, float thr, float ry, float rx, float x0, float y0,
+                            float x1, float y1)
+{
+    const float dxl = mx - x1, dxh = mx - x0;  // dx ranges over [dxl, dxh]
+    const float dyl = my - y1, dyh = my - y0;
+    const float xe = fminf(fmaxf(dxl, 0.0f), dxh);
+    const float ye = fminf(fmaxf(dyl, 0.0f), dyh);
+    const float ty = fminf(fmaxf(ry * xe, dyl), dyh);
+    const float tx = fminf(fmaxf(rx * ye, dxl), dxh);
+    const float p1 = cull_fma(c * ty, ty, cull_fma(b * xe, ty, (a * xe) * xe));
+    const float p2 = cull_fma(a * tx, tx, cull_fma(b * tx, ye, (c * ye) * ye));
+    const float mxa = fmaxf(fabsf(dxl), fabsf(dxh)), mya = fmaxf(fabsf(dyl), fabsf(dyh));
+    const float e   = cull_fma(c, mya * mya, a * (mxa * mxa));  // -(|a| ex + |c| ey)
+    const float margin = cull_fma(e, -4e-6f, 1e-6f);
+    return ry == ry && fmaxf(p1, p2) + margin < thr;
+}
+
 }  // namespace lcgs_b200

@@ -51,10 +51,12 @@ struct GlobalSh {
 
 __device__ __forceinline__ void write_record(float4* rec, const Splat2D& s, float op, const float* rgb)
 {
-    const float thr = alpha_threshold(op);
-    rec[0] = make_float4(s.px, s.py, -0.5f * s.conic[0], -s.conic[1]);
-    rec[1] = make_float4(-0.5f * s.conic[2], thr, op, INFINITY);
-    rec[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+    const float    thr = alpha_threshold(op);
+    const float    a = -0.5f * s.conic[0], b = -s.conic[1], c = -0.5f * s.conic[2];
+    const CullCoef k = cull_coef(s.px, s.py, a, b, c, thr);
+    rec[0] = make_float4(s.px, s.py, a, b);
+    rec[1] = make_float4(c, thr, op, k.ry);
+    rec[2] = make_float4(rgb[0], rgb[1], rgb[2], k.rx);
 }
 
 __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __grid_constant__ PreprocessArgs a)

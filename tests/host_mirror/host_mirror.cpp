@@ -43,15 +43,19 @@ __attribute__((visibility("default"))) void hm_preprocess(int P, int sh_deg, con
     }
 }
 
-// For n (Gaussian, rectangle) pairs: out[k] bit0 = cull_rect() says "drop", bit1 = some pixel centre
+// For n (Gaussian, rectangle) pairs: out[k] bit0 = cull_rect() (fast=0) or cull_rect_fast() (fast=1) says "drop", bit1 = some pixel centre
 // of the rectangle passes the exact per-pixel test (0 >= power >= thr).  bit0 && bit1 is a bug.
 __attribute__((visibility("default"))) void hm_cull_check(long n, const float* mean, const float* conic, const float* thr,
-                                                          const int* rect, unsigned char* out)
+                                                          const int* rect, int fast, unsigned char* out)
 {
     for (long k = 0; k < n; k++) {
         const float a = -0.5f * conic[3 * k], b = -conic[3 * k + 1], c = -0.5f * conic[3 * k + 2];
         const int   x0 = rect[4 * k], y0 = rect[4 * k + 1], x1 = rect[4 * k + 2], y1 = rect[4 * k + 3];
-        const bool  drop = cull_rect(mean[2 * k], mean[2 * k + 1], a, b, c, thr[k], (float)x0, (float)y0, (float)x1, (float)y1);
+        const bool  drop0 = cull_rect(mean[2 * k], mean[2 * k + 1], a, b, c, thr[k], (float)x0, (float)y0, (float)x1, (float)y1);
+        const CullCoef q  = cull_coef(mean[2 * k], mean[2 * k + 1], a, b, c, thr[k]);
+        const bool  drop1 = cull_rect_fast(mean[2 * k], mean[2 * k + 1], a, b, c, thr[k], q.ry, q.rx, (float)x0, (float)y0,
+                                           (float)x1, (float)y1);
+        const bool  drop  = fast ? drop1 : drop0;
         bool        any  = false;
         for (int y = y0; y <= y1 && !any; y++)
             for (int x = x0; x <= x1; x++) {

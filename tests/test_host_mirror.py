@@ -94,12 +94,13 @@ def test_cull_rect_is_conservative(hm):
         mean = np.ascontiguousarray(fr.means_2d[ids])
         conic = np.ascontiguousarray(fr.conic[ids])
         thr = np.ascontiguousarray(thr_all[ids])
-        out = np.zeros(n, np.uint8)
-        hm.hm_cull_check(C.c_long(n), _p(mean), _p(conic), _p(thr), _p(rect), _p(out))
-        assert not np.any(out == 3), "cull_rect dropped a contributing pair (%s)" % name
-        dropped, empty = np.mean(out & 1), np.mean((out & 2) == 0)
-        stats[name] = (dropped, empty)
-        assert dropped > 0.8 * empty - 0.01  # and it is tight: it finds most of the empty rectangles
+        for fast in (0, 1):  # the general test and the hoisted-division variant the blend kernel runs
+            out = np.zeros(n, np.uint8)
+            hm.hm_cull_check(C.c_long(n), _p(mean), _p(conic), _p(thr), _p(rect), C.c_int(fast), _p(out))
+            assert not np.any(out == 3), "cull_rect dropped a contributing pair (%s, fast=%d)" % (name, fast)
+            dropped, empty = np.mean(out & 1), np.mean((out & 2) == 0)
+            stats[name, fast] = (dropped, empty)
+            assert dropped > 0.8 * empty - 0.01  # and it is tight: it finds most of the empty rectangles
     print(stats)
     # adversarial: extremely elongated / huge / tiny Gaussians around random rectangles
     m = 200_000
@@ -115,6 +116,15 @@ def test_cull_rect_is_conservative(hm):
     y0 = rng.integers(0, 1060, m)
     rect = np.stack([x0, y0, x0 + rng.integers(0, 16, m), y0 + rng.integers(0, 16, m)], axis=1).astype(np.int32)
     thr = (-10 ** rng.uniform(-3, 0.75, m)).astype(np.float32)
-    out = np.zeros(m, np.uint8)
-    hm.hm_cull_check(C.c_long(m), _p(mean), _p(conic), _p(thr), _p(rect), _p(out))
-    assert not np.any(out == 3)
+    for fast in (0, 1):
+        out = np.zeros(m, np.uint8)
+        hm.hm_cull_check(C.c_long(m), _p(mean), _p(conic), _p(thr), _p(rect), C.c_int(fast), _p(out))
+        assert not np.any(out == 3)
+    # degenerate inputs are never culled by the fast variant: NaN threshold / mean, non-concave conic
+    bad_mean = np.array([[np.nan, 5.0], [np.inf, 5.0], [5.0, 5.0], [5.0, 5.0], [5000.0, 5000.0]], np.float32)
+    bad_conic = np.array([[1, 0, 1], [1, 0, 1], [-1, 0, 1], [1, 5, 1], [np.nan, 0, 1]], np.float32)
+    bad_thr = np.array([-1, -1, -1, -1, -1], np.float32)
+    bad_rect = np.tile(np.array([[100, 100, 107, 103]], np.int32), (5, 1))
+    out = np.zeros(5, np.uint8)
+    hm.hm_cull_check(C.c_long(5), _p(bad_mean), _p(bad_conic), _p(bad_thr), _p(bad_rect), C.c_int(1), _p(out))
+    assert not np.any(out & 1)
