@@ -251,6 +251,13 @@ LCGS_B200_API int lcgs_b200_stage_times(lcgs_b200_ctx* ctx, float ms[LCGS_B200_N
  * `num_passes` onesweep launches (passes_ms / num_passes = average launch duration). */
 LCGS_B200_API int lcgs_b200_sort_breakdown(lcgs_b200_ctx* ctx, float* histogram_ms, float* passes_ms, int* num_passes);
 
+/* ---- tuning hook (no reference counterpart) ---- */
+
+/* Makes kernels DROP parts of their work (bit mask, see kAblate* in csrc/common.cuh) so that the cost of
+ * one part can be measured on a real frame (scripts/ablate.py).  Results are wrong while the mask is
+ * non-zero; the default 0 is the only production value.  Process-wide. */
+LCGS_B200_API void lcgs_b200_debug_ablate(int mask);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,7 @@ _PROTOS = {
     "lcgs_b200_set_profiling": (_I, [_VP, _I]),
     "lcgs_b200_stage_times": (_I, [_VP, C.POINTER(_F)]),
     "lcgs_b200_sort_breakdown": (_I, [_VP, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I)]),
+    "lcgs_b200_debug_ablate": (None, [_I]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 

@@ -10,6 +10,7 @@
 //
 // Both are HBM-bound integer work: 12 bytes written per instance, 8 bytes read per instance.
 #include "common.cuh"
+#include "lookback.cuh"
 
 namespace lcgs_b200 {
 
@@ -85,85 +86,178 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// Fused-path emission: Gaussians are visited in depth order (order[k], sorted depth bits skeys[k]);
-// rects are the packed tile rects preprocess wrote (x0 | y0<<16, w | h<<16), offsets2 the inclusive
-// sum of the counts in that order.  Same warp-cooperative expansion as above.
-__global__ void __launch_bounds__(256)
+// Fused-path emission: Gaussians are visited in depth order (sorted (depth key, index) pairs); rects are
+// the packed tile rects preprocess wrote (x0 | y0<<16, w | h<<16).  One kernel does what used to be two
+// (an inclusive scan of the tile counts in depth order, then the emission): CTAs take tiles of 1024
+// Gaussians by ticket, chain the tile's instance count to its predecessors with a decoupled look-back
+// (lookback.cuh) and expand their Gaussians warp-cooperatively as above, 32 Gaussians per warp and step.
+// A ticket is only taken when the CTA is ready to load, count and publish at once: a tile that is held
+// back (e.g. taken ahead of time to prefetch it) stalls the look-back of every tile behind it.
+constexpr int kEmitThreads = 256;
+constexpr int kEmitWarps   = kEmitThreads / 32;
+constexpr int kEmitItems   = 4;  // Gaussians per thread and tile: chunk c of a warp is 32 consecutive ones
+constexpr int kEmitTile    = kEmitThreads * kEmitItems;
+
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kEmitThreads)
     duplicate_keys_sorted_kernel(const uint32_t* __restrict__ d_m, uint32_t m_capacity, uint32_t gx, uint32_t row0,
-                                 const uint32_t* __restrict__ order, const uint32_t* __restrict__ skeys,
-                                 const uint2* __restrict__ rects, const uint32_t* __restrict__ offsets2,
-                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, size_t capacity,
-                                 const __grid_constant__ SortDigits digits)
+                                 const __grid_constant__ SortedPairsU32 sorted, const uint2* __restrict__ rects,
+                                 unsigned long long* status, uint32_t* ticket, unsigned long long* __restrict__ keys,
+                                 uint32_t* __restrict__ vals, size_t capacity, const __grid_constant__ SortDigits digits,
+                                 bool exact_div, int ablate)
 {
     // digit histograms of the tile bits of the emitted keys (two passes at most: the tile sort then skips
     // its histogram kernel).  Consecutive lanes emit consecutive tiles of one Gaussian, so the upper digit
-    // is warp-aggregated with match_any.
+    // is aggregated per run of equal digits.
     __shared__ uint32_t s_hist[2 * 512];
-    const bool          do_hist = digits.hist != nullptr;
-    const int           nbins   = do_hist ? (digits.num_passes << digits.radix_bits) : 0;
-    for (int k = threadIdx.x; k < nbins; k += blockDim.x) s_hist[k] = 0u;
-    if (do_hist) __syncthreads();
-    const int      lane        = threadIdx.x & 31;
-    const long     warp_global = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long     num_warps   = ((long)gridDim.x * blockDim.x) >> 5;
-    const unsigned FULL        = 0xFFFFFFFFu;
-    uint32_t       M           = *d_m;
-    if (M > m_capacity) M = m_capacity;
+    __shared__ uint32_t s_wsum[kEmitWarps];
+    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_tk;
+    const bool     do_hist = digits.hist != nullptr && !(ablate & kAblateDupHist);
+    const int      nbins   = do_hist ? (digits.num_passes << digits.radix_bits) : 0;
+    const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xFFFFFFFFu;
+    for (int k = tid; k < nbins; k += kEmitThreads) s_hist[k] = 0u;
+    const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(s_hist);
+    const int      sh0 = digits.shift[0] - 32, sh1 = digits.shift[1] - 32;
+    const uint32_t m0 = digits.mask[0], m1 = digits.mask[1], hist1_addr = hist_addr + (4u << digits.radix_bits);
+    const bool     two_digits = digits.num_passes > 1;
 
-    for (long base = warp_global * 32; base < M; base += num_warps * 32) {
-        const long k   = base + lane;
-        uint32_t   cnt = 0, x0 = 0, y0 = 0, w = 1, dbits = 0, incl = 0, idx = 0;
-        if (k < M) {
-            incl          = __ldg(offsets2 + k);
-            idx           = __ldg(order + k);
-            dbits         = __ldg(skeys + k);
-            const uint2 r = __ldg(rects + idx);
-            x0            = r.x & 0xFFFFu;
-            y0            = r.x >> 16;
-            w             = r.y & 0xFFFFu;
-            cnt           = w * (r.y >> 16);
-            if (w == 0) w = 1;
-        }
-        uint32_t excl = __shfl_up_sync(FULL, incl, 1);
-        if (lane == 0) excl = (base > 0) ? __ldg(offsets2 + base - 1) : 0u;
-        uint32_t x = cnt;
+    uint32_t M = *d_m;
+    if (M > m_capacity) M = m_capacity;
+    const uint32_t num_tiles           = (M + kEmitTile - 1) / kEmitTile;
+    const bool     in_alt              = sorted_in_alt(sorted, M);
+    const uint32_t* __restrict__ order = in_alt ? sorted.alt_vals : sorted.vals;
+    const uint32_t* __restrict__ skeys = in_alt ? sorted.alt_keys : sorted.keys;
+    const unsigned le_mask             = (2u << lane) - 1u;  // lanes 0..lane (all ones for lane 31)
+
+    for (;;) {
+        __syncthreads();  // s_tk, s_wsum and s_base of the previous tile are no longer read
+        if (tid == 0) s_tk = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t t = s_tk;
+        if (t >= num_tiles) break;
+
+        // ---- load: (index, depth key) coalesced, then the rect gathers, all chunks in flight together ----
+        const uint32_t k0 = t * kEmitTile + warp * (32 * kEmitItems) + lane;
+        uint32_t       idx[kEmitItems], dbits[kEmitItems], xy0[kEmitItems], w[kEmitItems], cnt[kEmitItems];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(FULL, x, d);
-            if (lane >= d) x += y;
-        }
-        const uint32_t loc   = x - cnt;
-        const uint32_t total = __shfl_sync(FULL, x, 31);
-        for (uint32_t p0 = 0; p0 < total; p0 += 32) {
-            const uint32_t p = p0 + lane;
-            int            l = 0;
-#pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                const uint32_t v = __shfl_sync(FULL, loc, l + step);
-                if (v <= p) l += step;
+        for (int c = 0; c < kEmitItems; c++) {
+            const uint32_t k = k0 + 32 * c;
+            idx[c]           = 0xFFFFFFFFu;  // none
+            dbits[c]         = 0u;
+            if (k < M) {
+                idx[c]   = __ldg(order + k);
+                dbits[c] = __ldg(skeys + k) + kDepthKeyBase;  // keys are sorted relative to the base
             }
-            const uint32_t o_loc   = __shfl_sync(FULL, loc, l);
-            const uint32_t o_excl  = __shfl_sync(FULL, excl, l);
-            const uint32_t o_x0    = __shfl_sync(FULL, x0, l);
-            const uint32_t o_y0    = __shfl_sync(FULL, y0, l);
-            const uint32_t o_w     = __shfl_sync(FULL, w, l);
-            const uint32_t o_dbits = __shfl_sync(FULL, dbits, l);
-            const uint32_t o_idx   = __shfl_sync(FULL, idx, l);
-            if (p < total) {
-                const uint32_t j    = p - o_loc;
-                const uint32_t ry   = j / o_w;
-                const uint32_t rx   = j - ry * o_w;
-                const uint32_t tile = (o_x0 + rx) + (o_y0 + ry - row0) * gx;
-                const size_t   dst  = (size_t)o_excl + j;
-                if (dst < capacity) {
-                    keys[dst] = ((unsigned long long)tile << 32) | (unsigned long long)o_dbits;
-                    vals[dst] = o_idx;
-                    if (do_hist) {
-                        atomicAdd(&s_hist[(tile >> (digits.shift[0] - 32)) & digits.mask[0]], 1u);
-                        if (digits.num_passes > 1) {
-                            const uint32_t d1    = (tile >> (digits.shift[1] - 32)) & digits.mask[1];
-                            const unsigned peers = __match_any_sync(__activemask(), d1);
-                            if ((peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_hist[(1 << digits.radix_bits) + d1], (uint32_t)__popc(peers));
+        }
+#pragma unroll
+        for (int c = 0; c < kEmitItems; c++) {
+            uint2 r = make_uint2(0u, 0u);
+            if (idx[c] != 0xFFFFFFFFu) r = __ldg(rects + ((ablate & kAblateDupGather) ? k0 + 32 * c : idx[c]));
+            xy0[c] = r.x;
+            w[c]   = r.y & 0xFFFFu;
+            cnt[c] = w[c] * (r.y >> 16);
+            if (w[c] == 0u) w[c] = 1u;
+        }
+        // ---- count: inclusive scan inside each chunk, chunk bases inside the warp, totals across the CTA ----
+        uint32_t incl[kEmitItems], cbase[kEmitItems], wtot = 0;
+#pragma unroll
+        for (int c = 0; c < kEmitItems; c++) {
+            uint32_t x = cnt[c];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, x, d);
+                if (lane >= d) x += y;
+            }
+            incl[c]  = x;
+            cbase[c] = wtot;
+            wtot += __shfl_sync(FULL, x, 31);
+        }
+        if (lane == 0) s_wsum[warp] = wtot;
+        __syncthreads();
+        uint32_t wpre = 0, ttot = 0;
+#pragma unroll
+        for (int v = 0; v < kEmitWarps; v++) {
+            const uint32_t c = s_wsum[v];
+            if (v < warp) wpre += c;
+            ttot += c;
+        }
+        if (warp == 0) {
+            const uint32_t pre = lookback_warp_u32(status, t, ttot);
+            if (lane == 0) s_base = pre;
+        }
+        __syncthreads();
+        const uint32_t wbase = s_base + wpre;  // output offset of this warp's first instance
+
+        // ---- emit: a chunk's instances are one contiguous run of the output; slot p of the run goes to
+        // excl0 + p, loc = start of each Gaussian inside the run ------------------------------------------
+#pragma unroll
+        for (int c = 0; c < kEmitItems; c++) {
+            const bool     valid = idx[c] != 0xFFFFFFFFu;
+            const uint32_t excl0 = wbase + cbase[c];
+            const uint32_t total = __shfl_sync(FULL, incl[c], 31);
+            const uint32_t loc   = incl[c] - cnt[c];
+            // q = j / w as a multiply-high (exact while j * w < 2^32, checked on the host for the grid)
+            const uint32_t magic = (uint32_t)(0x100000000ull / w[c]) + 1u;
+            // Every compacted Gaussian touches a tile, so owners are consecutive lanes and an output slot
+            // finds its owner by counting the Gaussian starts at or before it: one ballot, one
+            // OR-reduction, two popc.
+            const bool dense = exact_div && __all_sync(FULL, !valid || cnt[c] > 0u);
+            for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+                const uint32_t p = p0 + lane;
+                int            l;
+                if (dense) {
+                    const unsigned before = __ballot_sync(FULL, valid && loc <= p0);
+                    const unsigned starts = __reduce_or_sync(FULL, (valid && loc > p0 && loc - p0 < 32u) ? 1u << (loc - p0) : 0u);
+                    l                     = __popc(before) - 1 + __popc(starts & le_mask);
+                } else {
+                    // owner = largest lane with loc <= p (zero-count lanes share their successor's loc and
+                    // are skipped because the search prefers the higher lane)
+                    l = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const uint32_t v = __shfl_sync(FULL, loc, l + step);
+                        if (v <= p) l += step;
+                    }
+                }
+                const uint32_t o_loc   = __shfl_sync(FULL, loc, l);
+                const uint32_t o_xy0   = __shfl_sync(FULL, xy0[c], l);
+                const uint32_t o_w     = __shfl_sync(FULL, w[c], l);
+                const uint32_t o_magic = __shfl_sync(FULL, magic, l);
+                const uint32_t o_dbits = __shfl_sync(FULL, dbits[c], l);
+                const uint32_t o_idx   = __shfl_sync(FULL, idx[c], l);
+                if (p < total) {
+                    const uint32_t j    = p - o_loc;
+                    const uint32_t ry   = exact_div ? (o_w == 1u ? j : __umulhi(j, o_magic)) : j / o_w;  // magic wraps for w == 1
+                    const uint32_t rx   = j - ry * o_w;
+                    const uint32_t tile = ((o_xy0 & 0xFFFFu) + rx) + ((o_xy0 >> 16) + ry - row0) * gx;
+                    const size_t   dst  = (size_t)excl0 + p;
+                    if (dst < capacity) {
+                        if (!(ablate & kAblateDupStores)) {
+                            keys[dst] = ((unsigned long long)tile << 32) | (unsigned long long)o_dbits;
+                            vals[dst] = o_idx;
+                        }
+                        if (do_hist) {
+                            red_shared_add(hist_addr + (((tile >> sh0) & m0) << 2), 1u);
+                            if (two_digits) {
+                                // the active lanes are a prefix of the warp and emit consecutive tiles: runs
+                                // of equal upper digits are counted by their first lane (MATCH.ANY is slow)
+                                const uint32_t d1      = (tile >> sh1) & m1;
+                                const unsigned act     = __activemask();
+                                const uint32_t prev    = __shfl_up_sync(act, d1, 1);
+                                const bool     lead    = lane == 0 || prev != d1;
+                                const unsigned leaders = __ballot_sync(act, lead);
+                                if (lead) {
+                                    const unsigned above = leaders & ~le_mask;
+                                    const int      end   = above ? __ffs(above) - 1 : __popc(act);
+                                    red_shared_add(hist1_addr + (d1 << 2), (uint32_t)(end - lane));
+                                }
+                            }
                         }
                     }
                 }
@@ -172,7 +266,7 @@ __global__ void __launch_bounds__(256)
     }
     if (do_hist) {
         __syncthreads();
-        for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
+        for (int k = tid; k < nbins; k += kEmitThreads) {
             const uint32_t c = s_hist[k];
             if (c) atomicAdd(digits.hist + k, c);
         }
@@ -246,9 +340,9 @@ int launch_duplicate_keys(lcgs_b200_ctx* ctx, int P, int W, int H, const float* 
     return LCGS_B200_OK;
 }
 
-int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, const uint32_t* order,
-                                 const uint32_t* skeys, const uint2* rects, const uint32_t* offsets2, uint64_t* keys,
-                                 uint32_t* vals, size_t capacity, int row0, const SortDigits* digits, cudaStream_t s)
+int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, const SortedPairsU32& sorted,
+                                 const uint2* rects, uint64_t* keys, uint32_t* vals, size_t capacity, int row0,
+                                 const SortDigits* digits, cudaStream_t s)
 {
     if (P <= 0) return LCGS_B200_OK;
     // fused histograms need the digits to live in the tile id (key bits >= 32) and at most two passes
@@ -256,14 +350,24 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
     if (digits && digits->hist && digits->num_passes >= 1 && digits->num_passes <= 2 && digits->radix_bits <= 9 &&
         digits->shift[0] >= 32)
         dg = *digits;
-    const uint32_t gx           = (uint32_t)((W + 15) / 16);
-    const long     warps_needed = ((long)P + 31) / 32;
-    long           blocks       = (warps_needed + 7) / 8;
-    const long     max_blocks   = (long)ctx->num_sms * 8;
-    if (blocks > max_blocks) blocks = max_blocks;
-    duplicate_keys_sorted_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, order, skeys, rects,
-                                                                 offsets2, reinterpret_cast<unsigned long long*>(keys), vals,
-                                                                 capacity, dg);
+    if (dg.num_passes < 2) dg.shift[1] = 32;  // unused, but keep the kernel's shift amounts in range
+    const uint32_t gx = (uint32_t)((W + 15) / 16);
+    // index inside a rect / rect width as a multiply-high: exact while j * w < 2^32; j < w * h and the
+    // packed rects hold 16-bit extents, so it is enough that gx * gx * 65535 stays below 2^32
+    const bool     exact_div = (unsigned long long)gx * gx * 65535ull < 0x100000000ull;
+    const uint32_t tiles     = (uint32_t)(((size_t)P + kEmitTile - 1) / kEmitTile);
+    int            rc        = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * sizeof(unsigned long long));
+    if (rc) return rc;
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->scan_ws.ptr, 0, (size_t)tiles * sizeof(unsigned long long), s));
+    uint32_t* ticket = ctx->d_scalars + LCGS_SCALAR_DUP_TICKET;
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
+    // persistent CTAs; tiles are handed out by ticket, so CTAs that are not resident yet hold nothing back
+    const uint32_t max_blocks = (uint32_t)ctx->num_sms * 6u;
+    const uint32_t blocks     = tiles < max_blocks ? tiles : max_blocks;
+    duplicate_keys_sorted_kernel<<<blocks, kEmitThreads, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, sorted, rects,
+                                                                (unsigned long long*)ctx->scan_ws.ptr, ticket,
+                                                                reinterpret_cast<unsigned long long*>(keys), vals, capacity,
+                                                                dg, exact_div, g_ablate);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }

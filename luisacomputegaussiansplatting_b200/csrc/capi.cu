@@ -95,7 +95,7 @@ static int check_frame_lists(lcgs_b200_ctx* ctx, const lcgs_b200_frame* fr)
 // Layout of the fused path's order workspace (all arrays have P entries).
 struct OrderWs {
     uint2*    rects;
-    uint32_t *ckeys, *cvals, *skeys, *svals, *offsets2;
+    uint32_t *ckeys, *cvals, *skeys, *svals;
 };
 static OrderWs order_ws_views(lcgs_b200_ctx* ctx, int P)
 {
@@ -107,7 +107,6 @@ static OrderWs order_ws_views(lcgs_b200_ctx* ctx, int P)
     o.cvals    = o.ckeys + n;
     o.skeys    = o.cvals + n;
     o.svals    = o.skeys + n;
-    o.offsets2 = o.svals + n;
     return o;
 }
 
@@ -124,20 +123,20 @@ static int splat_tail(lcgs_b200_ctx* ctx, int P, const lcgs_b200_frame* fr, cons
     if (depth_ordered) {
         const OrderWs o = order_ws_views(ctx, P);
         SortDigits    dg32, dg64;
-        // depth >= 0.2 > 0: the sign bit is clear, 31 key bits.  The compaction kernel also fills the
+        // Depth keys are stored relative to bits(0.2f) (kDepthKeyBase): 27 bits for any depth below
+        // 13107, so the fourth 9-bit pass normally skips itself.  The compaction kernel also fills the
         // depth sort's digit histograms, the emission kernel those of the tile sort.
-        if ((rc = sort_prepare_u32(ctx, (size_t)P, 0, 31, &dg32, s))) return rc;
+        if ((rc = sort_prepare_u32(ctx, (size_t)P, 0, 32, &dg32, s))) return rc;
         if ((rc = launch_scan_compact(ctx, fr->tiles_touched, fr->depth, P, fr->point_offsets, o.ckeys, o.cvals, d_n, d_m, &dg32, s)))
             return rc;
         mark(ctx, s);
         const bool hist32 = dg32.hist && dg32.num_passes <= 4;
-        if ((rc = sort_run_u32(ctx, o.ckeys, o.skeys, o.cvals, o.svals, d_m, (size_t)P, hist32, s))) return rc;
-        if ((rc = launch_scan_gather(ctx, o.svals, o.rects, d_m, P, o.offsets2, s))) return rc;
+        SortedPairsU32 sorted;
+        if ((rc = sort_run_u32(ctx, o.ckeys, o.skeys, o.cvals, o.svals, d_m, (size_t)P, hist32, &sorted, s))) return rc;
         mark(ctx, s);
         if ((rc = sort_prepare_u64(ctx, fr->list_capacity, 32, g.end_bit, &dg64, s))) return rc;
         const bool hist64 = dg64.hist && dg64.num_passes >= 1 && dg64.num_passes <= 2;
-        if ((rc = launch_duplicate_keys_sorted(ctx, d_m, P, g.W, o.svals, o.skeys, o.rects, o.offsets2,
-                                               fr->point_list_keys_unsorted, fr->point_list_unsorted, fr->list_capacity,
+        if ((rc = launch_duplicate_keys_sorted(ctx, d_m, P, g.W, sorted, o.rects, fr->point_list_keys_unsorted, fr->point_list_unsorted, fr->list_capacity,
                                                g.row0, hist64 ? &dg64 : nullptr, s)))
             return rc;
         mark(ctx, s);
@@ -171,13 +170,16 @@ static int splat_tail(lcgs_b200_ctx* ctx, int P, const lcgs_b200_frame* fr, cons
     return LCGS_B200_OK;
 }
 
+int g_ablate = 0;
+
 static int reserve_all(lcgs_b200_ctx* ctx, int P, size_t max_instances)
 {
     int rc;
     if (P > 0) {
         if ((rc = ws_reserve(ctx, ctx->record_ws, (size_t)P * kRecordFloat4s * sizeof(float4)))) return rc;
-        if ((rc = ws_reserve(ctx, ctx->scan_ws, (((size_t)P + 2047) / 2048) * 2 * sizeof(unsigned long long)))) return rc;
-        if ((rc = ws_reserve(ctx, ctx->order_ws, (size_t)P * 28))) return rc;
+        // look-back status: 2 chains x P/2048 tiles (scan + compaction), P/256 tiles (instance emission)
+        if ((rc = ws_reserve(ctx, ctx->scan_ws, (((size_t)P + 255) / 256) * sizeof(unsigned long long)))) return rc;
+        if ((rc = ws_reserve(ctx, ctx->order_ws, (size_t)P * 24))) return rc;
     }
     const size_t sort_items = max_instances > (size_t)(P > 0 ? P : 0) ? max_instances : (size_t)(P > 0 ? P : 0);
     if (sort_items > 0)
@@ -191,6 +193,8 @@ static int reserve_all(lcgs_b200_ctx* ctx, int P, size_t max_instances)
 extern "C" {
 
 int lcgs_b200_version(void) { return LCGS_B200_VERSION; }
+
+void lcgs_b200_debug_ablate(int mask) { lcgs_b200::g_ablate = mask; }
 
 const char* lcgs_b200_status_string(int status)
 {

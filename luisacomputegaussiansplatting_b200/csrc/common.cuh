@@ -18,6 +18,11 @@ constexpr int kNumSMs = 148;  // B200; the real count is queried at ctx creation
 //   r2 = (red, green, blue, cull quotient rx)            -- see cull_coef() in lcgs_math.cuh
 constexpr int kRecordFloat4s = 3;
 
+// Depth keys of the per-Gaussian sort are stored relative to the bit pattern of 0.2f, the smallest
+// depth a Gaussian that touches a tile can have (near cull, gs_projector/shader.cpp:121): for
+// depth < 0.2 * 2^16 they fit in 27 bits = three 9-bit digits, and the fourth pass skips itself.
+constexpr uint32_t kDepthKeyBase = 0x3E4CCCCDu;
+
 // Radix sort geometry (onesweep): 8-bit digits.
 constexpr int kRadixBits      = 8;
 constexpr int kRadix          = 1 << kRadixBits;
@@ -95,6 +100,12 @@ namespace lcgs_b200 {
 
 int ws_reserve(lcgs_b200_ctx* ctx, Workspace& ws, size_t bytes);
 
+// Tuning hook (lcgs_b200_debug_ablate): bits that make a kernel DROP one part of its work so that the
+// part's cost can be measured on the real frame.  Results are wrong while any bit is set; 0 in production.
+extern int g_ablate;
+constexpr int kAblateSortStores = 1, kAblateSortLookback = 2, kAblateDupHist = 4, kAblateDupStores = 8, kAblateDupGather = 16,
+              kAblateCompactHist = 32, kAblateCompactDepth = 64;
+
 // stage launchers (one group per .cu); all enqueue on `s` and return an lcgs_b200_status
 int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b200_view_params* vp,
                             const lcgs_b200_frame* fr, float4* records, uint2* rects, cudaStream_t s);
@@ -102,11 +113,10 @@ struct SortDigits;
 int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const float* depth, int P, uint32_t* offsets,
                         uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, const SortDigits* digits,
                         cudaStream_t s);
-int launch_scan_gather(lcgs_b200_ctx* ctx, const uint32_t* order, const uint2* rects, const uint32_t* d_n, int capacity,
-                       uint32_t* offsets2, cudaStream_t s);
-int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, const uint32_t* order,
-                                 const uint32_t* skeys, const uint2* rects, const uint32_t* offsets2, uint64_t* keys,
-                                 uint32_t* vals, size_t capacity, int row0, const SortDigits* digits, cudaStream_t s);
+struct SortedPairsU32;
+int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, const SortedPairsU32& sorted,
+                                 const uint2* rects, uint64_t* keys, uint32_t* vals, size_t capacity, int row0,
+                                 const SortDigits* digits, cudaStream_t s);
 // digit layout of a prepared sort, for kernels that accumulate its histograms while producing the keys
 struct SortDigits {
     uint32_t* hist;  // [num_passes][1 << radix_bits], zeroed
@@ -116,8 +126,14 @@ struct SortDigits {
 };
 void sort_free_plans(lcgs_b200_ctx* ctx);
 int sort_prepare_u32(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s);
-int sort_run_u32(lcgs_b200_ctx* ctx, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
-                 const uint32_t* d_n, size_t capacity, bool hist_ready, cudaStream_t s);
+// Where a u32 sort left its result: (keys, vals), or (alt_keys, alt_vals) when the last pass found all
+// its keys in digit 0 and skipped itself -- the case iff last_hist && *last_hist == n (device-side test).
+struct SortedPairsU32 {
+    const uint32_t *keys, *vals, *alt_keys, *alt_vals, *last_hist;
+};
+__device__ __forceinline__ bool sorted_in_alt(const SortedPairsU32& r, uint32_t n) { return r.last_hist && __ldg(r.last_hist) == n; }
+int sort_run_u32(lcgs_b200_ctx* ctx, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
+                 const uint32_t* d_n, size_t capacity, bool hist_ready, SortedPairsU32* res, cudaStream_t s);
 int sort_prepare_u64(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s);
 int sort_run_u64(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
                  const uint32_t* d_n, size_t capacity, bool hist_ready, cudaStream_t s);

@@ -5,24 +5,9 @@
 //
 // HBM-bound: 8 bytes per item (one 4-byte read, one 4-byte write), 16-byte vector accesses.
 #include "common.cuh"
+#include "lookback.cuh"
 
 namespace lcgs_b200 {
-
-// tile status word: (flag << 32) | value, flag 0 = empty, 1 = tile aggregate, 2 = inclusive prefix
-constexpr unsigned long long kFlagAggregate = 1ull << 32;
-constexpr unsigned long long kFlagInclusive = 2ull << 32;
-
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 __global__ void __launch_bounds__(kScanThreads)
     scan_inclusive_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t num_tiles,
@@ -80,22 +65,12 @@ __global__ void __launch_bounds__(kScanThreads)
         tile_sum += x;
     }
 
-    if (tid == 0) {
-        uint32_t prefix = 0;
-        if (tile > 0) {
-            st_status(status + tile, kFlagAggregate | tile_sum);
-            int p = (int)tile - 1;
-            for (;;) {
-                unsigned long long st;
-                do { st = ld_status(status + p); } while ((st >> 32) == 0ull);
-                prefix += (uint32_t)st;
-                if ((st >> 32) == 2ull) break;
-                --p;
-            }
+    if (warp == 0) {
+        const uint32_t prefix = lookback_warp_u32(status, tile, tile_sum);
+        if (lane == 0) {
+            s_tile_prefix = prefix;
+            if (tile == num_tiles - 1 && d_total) *d_total = prefix + tile_sum;
         }
-        st_status(status + tile, kFlagInclusive | (unsigned long long)(prefix + tile_sum));
-        s_tile_prefix = prefix;
-        if (tile == num_tiles - 1 && d_total) *d_total = prefix + tile_sum;
     }
     __syncthreads();
     const uint32_t add = s_tile_prefix + warp_prefix;
@@ -122,8 +97,8 @@ __global__ void __launch_bounds__(kScanThreads)
 // index order, so sorted keys, sorted values and ranges are bit-identical to the reference's.
 //
 // scan_compact_kernel: point_offsets (inclusive sum of tiles_touched, the reference's output) AND a
-// stable compaction of the Gaussians that touch a tile into (depth bits, index) pairs.
-// scan_gather_kernel: inclusive sum of the tile counts taken in depth order (offsets of the emission).
+// stable compaction of the Gaussians that touch a tile into (depth bits, index) pairs.  The offsets of
+// the emission in depth order are chained inside the emission kernel itself (binning.cu).
 
 struct ScanPair {
     uint32_t a, b;
@@ -154,25 +129,6 @@ __device__ __forceinline__ ScanPair block_scan_pair(ScanPair v, ScanPair* s_warp
     return ScanPair{ pre.a + xa - v.a, pre.b + xb - v.b };
 }
 
-// decoupled look-back of one chained sum by one thread; publishes aggregate then inclusive
-__device__ __forceinline__ uint32_t lookback_u32(unsigned long long* status, uint32_t tile, uint32_t tile_sum)
-{
-    uint32_t prefix = 0;
-    if (tile > 0) {
-        st_status(status + tile, kFlagAggregate | tile_sum);
-        int p = (int)tile - 1;
-        for (;;) {
-            unsigned long long st;
-            do { st = ld_status(status + p); } while ((st >> 32) == 0ull);
-            prefix += (uint32_t)st;
-            if ((st >> 32) == 2ull) break;
-            --p;
-        }
-    }
-    st_status(status + tile, kFlagInclusive | (unsigned long long)(prefix + tile_sum));
-    return prefix;
-}
-
 constexpr int kCompactItems = 8;                          // per thread
 constexpr int kCompactTile  = kScanThreads * kCompactItems;  // 2048 Gaussians per CTA
 
@@ -180,11 +136,11 @@ __global__ void __launch_bounds__(kScanThreads)
     scan_compact_kernel(const uint32_t* __restrict__ tiles_touched, const float* __restrict__ depth, uint32_t n,
                         uint32_t num_tiles, uint32_t* __restrict__ offsets, uint32_t* __restrict__ ckeys,
                         uint32_t* __restrict__ cvals, unsigned long long* status_sum, unsigned long long* status_cnt,
-                        uint32_t* ticket, uint32_t* d_total, uint32_t* d_count, const __grid_constant__ SortDigits digits)
+                        uint32_t* ticket, uint32_t* d_total, uint32_t* d_count, const __grid_constant__ SortDigits digits, int ablate)
 {
     // digit histograms of the depth keys this CTA compacts (the depth sort then skips its histogram kernel)
     __shared__ uint32_t s_hist[4 * 512];
-    const bool          do_hist = digits.hist != nullptr;
+    const bool          do_hist = digits.hist != nullptr && !(ablate & kAblateCompactHist);
     const int           nbins   = do_hist ? (digits.num_passes << digits.radix_bits) : 0;
     for (int k = threadIdx.x; k < nbins; k += kScanThreads) s_hist[k] = 0u;
     __shared__ uint32_t s_tile;
@@ -214,8 +170,11 @@ __global__ void __launch_bounds__(kScanThreads)
     }
     ScanPair       tot;
     const ScanPair excl = block_scan_pair(mine, s_warp, &tot);
-    if (tid == 0) s_prefix[0] = lookback_u32(status_sum, tile, tot.a);
-    if (tid == 32) s_prefix[1] = lookback_u32(status_cnt, tile, tot.b);
+    // two chains (instance sum, touching-Gaussian count), one warp each
+    if (tid < 64) {
+        const uint32_t pre = (tid < 32) ? lookback_warp_u32(status_sum, tile, tot.a) : lookback_warp_u32(status_cnt, tile, tot.b);
+        if ((tid & 31) == 0) s_prefix[tid >> 5] = pre;
+    }
     __syncthreads();
     uint32_t sum = s_prefix[0] + excl.a, cnt = s_prefix[1] + excl.b;
     if (tile == num_tiles - 1 && tid == 0) {
@@ -228,7 +187,7 @@ __global__ void __launch_bounds__(kScanThreads)
         sum += v[k];
         out[k] = sum;
         if (v[k] > 0u) {  // stable compaction: slots are handed out in index order
-            const uint32_t key = __float_as_uint(__ldg(depth + e0 + k));
+            const uint32_t key = ((ablate & kAblateCompactDepth) ? (e0 + k) * 2654435761u : __float_as_uint(__ldg(depth + e0 + k))) - kDepthKeyBase;
             ckeys[cnt] = key;
             cvals[cnt] = e0 + k;
             cnt++;
@@ -256,55 +215,6 @@ __global__ void __launch_bounds__(kScanThreads)
     }
 }
 
-// offsets2[k] = inclusive sum over k of the tile count of Gaussian order[k] (count = rect area)
-__global__ void __launch_bounds__(kScanThreads)
-    scan_gather_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rects, const uint32_t* __restrict__ d_n,
-                       uint32_t capacity, uint32_t* __restrict__ offsets2, unsigned long long* status, uint32_t* ticket)
-{
-    __shared__ uint32_t s_tile;
-    __shared__ ScanPair s_warp[kScanThreads / 32];
-    __shared__ uint32_t s_prefix;
-    const int      tid       = threadIdx.x;
-    uint32_t       n         = *d_n;
-    if (n > capacity) n = capacity;
-    const uint32_t num_tiles = (n + kCompactTile - 1) / kCompactTile;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= num_tiles) return;
-        // striped arrangement: coalesced index loads, the rect gathers hit L2
-        uint32_t v[kCompactItems];
-#pragma unroll
-        for (int k = 0; k < kCompactItems; k++) {
-            const uint32_t e = tile * kCompactTile + k * kScanThreads + tid;
-            v[k]             = 0u;
-            if (e < n) {
-                const uint2 r = __ldg(rects + __ldg(order + e));
-                v[k]          = (r.y & 0xFFFFu) * (r.y >> 16);
-            }
-        }
-        // scan in element order: element e = tile*2048 + k*256 + tid -> k-major
-        ScanPair tot;
-        uint32_t excl[kCompactItems], carry = 0;
-#pragma unroll
-        for (int k = 0; k < kCompactItems; k++) {
-            const ScanPair x = block_scan_pair(ScanPair{ v[k], 0u }, s_warp, &tot);
-            excl[k]          = carry + x.a;
-            carry += tot.a;
-        }
-        if (tid == 0) s_prefix = lookback_u32(status, tile, carry);
-        __syncthreads();
-        const uint32_t pre = s_prefix;
-#pragma unroll
-        for (int k = 0; k < kCompactItems; k++) {
-            const uint32_t e = tile * kCompactTile + k * kScanThreads + tid;
-            if (e < n) offsets2[e] = pre + excl[k] + v[k];
-        }
-    }
-}
-
 int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const float* depth, int P, uint32_t* offsets,
                         uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, const SortDigits* digits,
                         cudaStream_t s)
@@ -325,24 +235,7 @@ int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
     auto* st = (unsigned long long*)ctx->scan_ws.ptr;
     scan_compact_kernel<<<tiles, kScanThreads, 0, s>>>(tiles_touched, depth, (uint32_t)P, tiles, offsets, ckeys, cvals, st,
-                                                       st + tiles, ticket, d_total, d_count, dg);
-    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
-    return LCGS_B200_OK;
-}
-
-int launch_scan_gather(lcgs_b200_ctx* ctx, const uint32_t* order, const uint2* rects, const uint32_t* d_n, int capacity,
-                       uint32_t* offsets2, cudaStream_t s)
-{
-    if (capacity <= 0) return LCGS_B200_OK;
-    const uint32_t tiles = (uint32_t)(((size_t)capacity + kCompactTile - 1) / kCompactTile);
-    int            rc    = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * 2 * sizeof(unsigned long long));
-    if (rc) return rc;
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->scan_ws.ptr, 0, (size_t)tiles * sizeof(unsigned long long), s));
-    uint32_t* ticket = ctx->d_scalars + LCGS_SCALAR_SCAN_TICKET;
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
-    const uint32_t blocks = tiles < (uint32_t)ctx->num_sms * 8u ? tiles : (uint32_t)ctx->num_sms * 8u;
-    scan_gather_kernel<<<blocks, kScanThreads, 0, s>>>(order, rects, d_n, (uint32_t)capacity, offsets2,
-                                                      (unsigned long long*)ctx->scan_ws.ptr, ticket);
+                                                       st + tiles, ticket, d_total, d_count, dg, g_ablate);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }

@@ -25,6 +25,9 @@ constexpr uint32_t kStatusAggregate = 1u << 30;
 constexpr uint32_t kStatusInclusive = 2u << 30;
 constexpr uint32_t kStatusValueMask = (1u << 30) - 1u;
 constexpr int      kLookbackWindow  = 8;
+// onesweep_pass_kernel flags.  The Ablate* bits (lcgs_b200_debug_ablate, tuning only) produce WRONG results:
+// they drop one phase so that its share of the pass can be measured.
+constexpr int kSweepSkipIfTrivial = 1, kSweepAblateStores = 2, kSweepAblateLookback = 4;
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
 {
@@ -128,14 +131,16 @@ constexpr size_t sweep_smem_bytes()
            64;
 }
 
-// lanes holding the same digit as this lane: MATCH.ANY, or RBITS ballots (+1 for the "invalid" flag)
-template <int RBITS, bool USE_MATCH>
+// lanes holding the same digit as this lane: MATCH.ANY, or one ballot per digit bit (BITS = RBITS, +1 for
+// the "invalid" flag of a partial tile).  MATCH.ANY is the slower of the two on sm_100a (measured on the
+// C3 tile sort: 0.368 ms with MATCH, 0.337 ms with 8 ballots per item).
+template <int BITS, bool USE_MATCH>
 __device__ __forceinline__ unsigned digit_peers(uint32_t d)
 {
     if (USE_MATCH) return __match_any_sync(0xFFFFFFFFu, d);
     unsigned peers = 0xFFFFFFFFu;
 #pragma unroll
-    for (int b = 0; b <= RBITS; b++) {
+    for (int b = 0; b < BITS; b++) {
         const bool     bit = (d >> b) & 1u;
         const unsigned m   = __ballot_sync(0xFFFFFFFFu, bit);
         peers &= bit ? m : ~m;
@@ -149,13 +154,15 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                          const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
                          const uint32_t* __restrict__ d_n, size_t capacity, const uint32_t* __restrict__ hist /* [RADIX] */,
                          uint32_t* status /* [tiles][RADIX] */, uint32_t* ticket, int shift, uint32_t mask,
-                         unsigned long long* dbg /* optional phase timers, LCGS_SORT_DEBUG=1 */)
+                         int flags /* kSweep* */, unsigned long long* dbg /* optional phase timers, LCGS_SORT_DEBUG=1 */)
 {
     constexpr int RADIX = 1 << RBITS;
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE  = THREADS * ITEMS;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit");
     static_assert((WARPS * RADIX) % THREADS == 0, "counter zeroing");
+    static_assert(RADIX % 32 == 0 && THREADS * ITEMS <= 65536, "digit warps are whole warps; tile slots fit 16 bits");
+
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyT* const               s_keys   = reinterpret_cast<KeyT*>(smem_raw);
     uint32_t* const           s_vals   = reinterpret_cast<uint32_t*>(s_keys + TILE);
@@ -165,7 +172,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     uint32_t* const           s_ticket = s_scan + WARPS;  // [2]
 
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned FULLM     = 0xFFFFFFFFu;
     const unsigned lt_mask   = (1u << lane) - 1u;
     const size_t   n         = resolve_n(n_host, d_n, capacity);
     const uint32_t num_tiles = (uint32_t)((n + TILE - 1) / TILE);
@@ -173,6 +179,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const bool     is_digit  = tid < RADIX;
     const bool     hi_word   = shift >= 32;  // uniform: the digit lives entirely in the key's high word
     uint32_t* const my_hist  = s_wh + warp * RADIX;
+    // every key has digit 0 in this pass (the top bits of the depth keys): the pass is the identity
+    // permutation; the consumers of the sorted list make the same test and read this pass's input
+    if ((flags & kSweepSkipIfTrivial) && __ldg(hist) == (uint32_t)n) return;
+    const bool ablate_stores = flags & kSweepAblateStores, ablate_lookback = flags & kSweepAblateLookback;  // tuning only
 
     auto digit_of = [&](KeyT k) -> uint32_t {
         return hi_word ? key_digit_hi(k, shift, mask) : key_digit(k, shift, mask);
@@ -223,42 +233,35 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         const bool     full   = nvalid == (uint32_t)TILE;
         if (tid == 0) s_ticket[1] = atomicAdd(ticket, 1u);  // published by the barrier after ranking
 
-        // ---- rank inside the warp with match_any (s_wh is zero on entry) -------------------------
-        uint32_t rank[ITEMS];
-        if (full) {
+        // ---- rank inside the warp (s_wh is zero on entry): lanes with the same digit are found with
+        // match_any; the lowest of them adds the group to the warp's counter with ONE shared-memory atomic
+        // and hands the old value to its peers by shuffle.  No register dependency between the items (the
+        // same-address atomics of a warp execute in program order), so the 8 chains overlap.
+        uint32_t rd[ITEMS];  // (digit << 16) | rank inside (warp, digit); after the scatter: slot in the tile
 #pragma unroll
-            for (int j = 0; j < ITEMS; j++) {
-                const uint32_t d     = digit_of(key[j]);
-                const unsigned peers = digit_peers<RBITS, USE_MATCH>(d);
-                const unsigned lower = peers & lt_mask;
-                const uint32_t pre   = my_hist[d];
-                __syncwarp();
-                if (lower == 0u) my_hist[d] = pre + __popc(peers);
-                __syncwarp();
-                rank[j] = pre + __popc(lower);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < ITEMS; j++) {
-                const bool     valid = q0 + 32 * j < nvalid;
-                const uint32_t d     = valid ? digit_of(key[j]) : (uint32_t)RADIX;
-                const unsigned peers = digit_peers<RBITS, USE_MATCH>(d);
-                const unsigned lower = peers & lt_mask;
-                uint32_t       pre   = 0;
-                if (valid) pre = my_hist[d];
-                __syncwarp();
-                if (valid && lower == 0u) my_hist[d] = pre + __popc(peers);
-                __syncwarp();
-                rank[j] = pre + __popc(lower);
-            }
+        for (int j = 0; j < ITEMS; j++) {
+            const bool     valid  = full || q0 + 32 * j < nvalid;
+            const uint32_t d      = valid ? digit_of(key[j]) : (uint32_t)RADIX;
+            const unsigned peers  = full ? digit_peers<RBITS, USE_MATCH>(d) : digit_peers<RBITS + 1, USE_MATCH>(d);
+            const unsigned lower  = peers & lt_mask;
+            uint32_t       before = 0;
+            if (valid && lower == 0u) before = atomicAdd(&my_hist[d], (uint32_t)__popc(peers));
+            before = __shfl_sync(0xFFFFFFFFu, before, __ffs(peers) - 1);
+            rd[j]  = (d << 16) | (before + __popc(lower));
         }
         __syncthreads();
         lap(0);  // wait for keys + rank
         const uint32_t next_tile = s_ticket[1];
 
+        // ---- the values are requested now and scattered next to their keys after the digit scan ------
+        uint32_t        val[ITEMS];
+        const uint32_t* vsrc = vals_in + (size_t)tile * TILE + q0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) val[j] = (full || q0 + 32 * j < nvalid) ? __ldg(vsrc + 32 * j) : 0u;
+
         // ---- per digit (thread d): tile histogram, early publish, first look-back window ---------
         constexpr bool  kCntInRegs = WARPS <= 16;  // otherwise re-read the counters instead of holding them
-        uint32_t        tile_count = 0;
+        uint32_t        tile_count = 0, scan_incl = 0;
         uint32_t        cnt[kCntInRegs ? WARPS : 1];
         uint32_t        st[kLookbackWindow];
         uint32_t* const my_status = status + (size_t)tile * RADIX + tid;
@@ -271,13 +274,26 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 tile_count += c;
             }
             if (tile > 0) st_relaxed_u32(my_status, kStatusAggregate | tile_count);
-            // the predecessors' status words are requested now and consumed after the key scatter
+            // the predecessors' status words are requested now and consumed after the scatter
 #pragma unroll
             for (int k = 0; k < kLookbackWindow; k++)
                 st[k] = (p - k >= 0) ? ld_relaxed_u32(status + (size_t)(p - k) * RADIX + tid) : kStatusInclusive;
+            // exclusive scan of the digit counts: only the RADIX / 32 digit warps take part
+            scan_incl = tile_count;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, scan_incl, d);
+                if (lane >= d) scan_incl += y;
+            }
+            if (lane == 31) s_scan[warp] = scan_incl;
         }
-        const uint32_t tile_start = block_exclusive_scan<THREADS>(tile_count, s_scan);
+        __syncthreads();
+        uint32_t tile_start = 0;
         if (is_digit) {
+#pragma unroll
+            for (int w = 0; w < RADIX / 32; w++)
+                if (w < warp) tile_start += s_scan[w];
+            tile_start += scan_incl - tile_count;
             uint32_t run = tile_start;
 #pragma unroll
             for (int w = 0; w < WARPS; w++) {
@@ -287,29 +303,35 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             }
         }
         __syncthreads();
-        lap(1);  // digit prefix + block scan
+        lap(1);  // digit prefix + scan
 
-        // ---- scatter keys into shared memory in tile-sorted order --------------------------------
+        // ---- scatter keys and values into shared memory in tile-sorted order ---------------------
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             if (full || q0 + 32 * j < nvalid) {
-                rank[j] += my_hist[digit_of(key[j])];
-                s_keys[rank[j]] = key[j];
+                const uint32_t slot = (rd[j] & 0xFFFFu) + my_hist[rd[j] >> 16];
+                s_keys[slot] = key[j];
+                s_vals[slot] = val[j];
             }
         }
-        lap(2);  // scatter keys
+        // this warp's counters are free again: clear them for its next tile (only the warp itself touches
+        // them until the barrier after the next ranking)
+        __syncwarp();
+#pragma unroll
+        for (int k = lane; k < RADIX; k += 32) my_hist[k] = 0u;
+        // the key registers are free: request the next tile's keys behind the look-back and the write-out
+        load_keys(next_tile);
+        lap(2);  // scatter
 
         // ---- decoupled look-back: consume the window requested above, then further windows ---------
         if (is_digit) {
             uint32_t prefix = 0;
-            bool     more   = tile > 0;
+            bool     more   = tile > 0 && !ablate_lookback;
             while (more) {
-                if (dbg && tid == 0) atomicAdd(dbg + 8, 1ull);
 #pragma unroll
                 for (int k = 0; k < kLookbackWindow; k++) {
                     if (!more) break;
                     if ((st[k] >> 30) == 0u) {  // not published yet: poll again from this tile
-                        if (dbg && tid == 0) atomicAdd(dbg + 9, 1ull);
                         p -= k;
                         break;
                     }
@@ -328,44 +350,26 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         }
         lap(3);  // thread 0's own look-back
 
-        // ---- start the value loads of this tile and the key loads of the next one ----------------
-        uint32_t        val[ITEMS];
-        const uint32_t* vsrc = vals_in + (size_t)tile * TILE + q0;
-#pragma unroll
-        for (int j = 0; j < ITEMS; j++) val[j] = (full || q0 + 32 * j < nvalid) ? __ldg(vsrc + 32 * j) : 0u;
-        load_keys(next_tile);
         __syncthreads();
-        lap(4);  // issue loads + wait for the slowest digit's look-back
+        lap(4);  // wait for the slowest digit's look-back
 
-        // ---- coalesced key write-out (remember each slot's destination), scatter the values --------
-        uint32_t dst[ITEMS];
+        // ---- coalesced write-out of keys and values ------------------------------------------------
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             const uint32_t q = tid + j * THREADS;
-            if (full || q < nvalid) {
-                const KeyT k     = s_keys[q];
-                dst[j]           = s_base[digit_of(k)] + q;
-                keys_out[dst[j]] = k;
+            if ((full || q < nvalid) && !ablate_stores) {
+                const KeyT     k   = s_keys[q];
+                const uint32_t dst = s_base[digit_of(k)] + q;
+                keys_out[dst]      = k;
+                vals_out[dst]      = s_vals[q];
             }
-        }
-#pragma unroll
-        for (int j = 0; j < ITEMS; j++)
-            if (full || q0 + 32 * j < nvalid) s_vals[rank[j]] = val[j];
-        // the per-warp counters are free again: clear them for the next tile
-#pragma unroll
-        for (int k = 0; k < (WARPS * RADIX) / THREADS; k++) s_wh[tid + k * THREADS] = 0u;
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < ITEMS; j++) {
-            const uint32_t q = tid + j * THREADS;
-            if (full || q < nvalid) vals_out[dst[j]] = s_vals[q];
         }
         lap(5);  // write-out
         if (dbg && tid == 0) atomicAdd(dbg + 10, 1ull);
         tile = next_tile;
         // s_ticket[1] is rewritten at the next loop top, after every thread has read it (three barriers
-        // ago); s_keys / s_vals are rewritten after two more barriers, by which time every thread has
-        // finished the loops above
+        // ago); s_keys / s_vals are rewritten after three more barriers, by which time every thread has
+        // finished the loop above; s_scan is rewritten before the next barrier, read before the last one
     }
 }
 
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(256)
 template <typename KeyT>
 struct SweepVariant {
     void (*kernel)(const KeyT*, KeyT*, const uint32_t*, uint32_t*, size_t, const uint32_t*, size_t, const uint32_t*, uint32_t*,
-                   uint32_t*, int, uint32_t, unsigned long long*);
+                   uint32_t*, int, uint32_t, int, unsigned long long*);
     int         threads, tile, radix_bits, blocks_per_sm;
     size_t      smem;
     const char* name;
@@ -411,6 +415,14 @@ static const SweepVariant<unsigned long long> kSweep64[] = {
     LCGS_SWEEP(unsigned long long, 1024, 12, 7, 1, true), // 12: one 12288-pair tile per SM
     LCGS_SWEEP(unsigned long long, 1024, 16, 7, 1, true), // 13: one 16384-pair tile per SM
     LCGS_SWEEP(unsigned long long, 1024, 8, 7, 1, true),  // 14
+    LCGS_SWEEP(unsigned long long, 512, 8, 7, 2, false),  // 15: ballot ranking instead of MATCH.ANY
+    LCGS_SWEEP(unsigned long long, 256, 16, 7, 3, false), // 16
+    LCGS_SWEEP(unsigned long long, 512, 8, 9, 2, false),  // 17
+    LCGS_SWEEP(unsigned long long, 256, 16, 7, 4, false), // 18
+    LCGS_SWEEP(unsigned long long, 256, 12, 7, 4, false), // 19
+    LCGS_SWEEP(unsigned long long, 256, 8, 7, 6, false),  // 20
+    LCGS_SWEEP(unsigned long long, 128, 16, 7, 8, false), // 21
+    LCGS_SWEEP(unsigned long long, 256, 20, 7, 2, false), // 22
 };
 // 32-bit depth keys of the per-Gaussian sort
 static const SweepVariant<uint32_t> kSweep32[] = {
@@ -419,8 +431,14 @@ static const SweepVariant<uint32_t> kSweep32[] = {
     LCGS_SWEEP(uint32_t, 256, 16, 8, 3, true),
     LCGS_SWEEP(uint32_t, 512, 4, 9, 3, true),
     LCGS_SWEEP(uint32_t, 256, 8, 8, 4, true),
+    LCGS_SWEEP(uint32_t, 512, 8, 9, 2, false),  // 5: ballot ranking
+    LCGS_SWEEP(uint32_t, 512, 8, 9, 3, false),  // 6
+    LCGS_SWEEP(uint32_t, 512, 4, 9, 4, false),  // 7
+    LCGS_SWEEP(uint32_t, 512, 12, 9, 2, false), // 8
+    LCGS_SWEEP(uint32_t, 512, 16, 9, 1, false), // 9
 };
 constexpr int kMinSweepTile = 2048;
+constexpr size_t kHistSlotBytes = (size_t)kMaxSortPasses * kMaxRadix * sizeof(uint32_t);  // 16 KB, 256-byte multiple
 
 template <typename KeyT>
 struct SweepTable;
@@ -449,17 +467,19 @@ static int sweep_variant_index(int bits)
         if (e && atoi(e) >= 0 && atoi(e) < SweepTable<KeyT>::count()) env_idx = atoi(e);
     }
     if (env_idx >= 0) return env_idx;
-    if (sizeof(KeyT) == 8 && bits <= 14) return 8;
-    return 0;
+    if (sizeof(KeyT) == 8) return bits <= 14 ? 19 : 0;  // 7-bit tile digits, 256 x 12, 4 CTAs/SM, ballots | 9-bit, MATCH
+    return 9;                                            // depth keys: 9-bit digits, one 8192-pair tile per SM
 }
 
-// workspace layout: [hist: passes*512 u32][status: passes*tiles*RADIX u32][tmp keys][tmp vals]
+// workspace layout: [hist slot 0][hist slot 1][status: passes*tiles*RADIX u32][tmp keys][tmp vals], a
+// hist slot being [kMaxSortPasses][512] u32.  The depth sort of the fused frame uses slot 0, every other
+// sort slot 1: the consumers of the depth-sorted list still read the depth sort's last histogram (to
+// learn whether its last pass skipped itself) after the tile sort has been prepared.
 static size_t sort_ws_layout(size_t n, size_t key_bytes, size_t* off_status, size_t* off_keys, size_t* off_vals)
 {
     const size_t tiles = (n + kMinSweepTile - 1) / kMinSweepTile;
     size_t       off   = 0;
-    off += (size_t)kMaxSortPasses * kMaxRadix * sizeof(uint32_t);
-    off = (off + 255) & ~(size_t)255;
+    off += 2 * kHistSlotBytes;
     if (off_status) *off_status = off;
     off += (size_t)kMaxSortPasses * tiles * kMaxRadix * sizeof(uint32_t);
     off = (off + 255) & ~(size_t)255;
@@ -489,7 +509,7 @@ struct SortPlan {
 // launch_sort_t can be told to skip its own histogram kernel.
 template <typename KeyT>
 static int sort_prepare_t(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, uint32_t* ticket, SortPlan<KeyT>* plan,
-                          cudaStream_t s)
+                          cudaStream_t s, int hist_slot = 1)
 {
     constexpr int kKeyBits = (int)sizeof(KeyT) * 8;
     LCGS_REQUIRE(ctx, begin_bit >= 0 && end_bit <= kKeyBits && begin_bit <= end_bit, "sort: bad bit range");
@@ -519,20 +539,26 @@ static int sort_prepare_t(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int e
     int          rc    = ws_reserve(ctx, ctx->sort_ws, bytes);
     if (rc) return rc;
     char* ws       = (char*)ctx->sort_ws.ptr;
-    plan->hist     = (uint32_t*)ws;
+    plan->hist     = (uint32_t*)(ws + (size_t)hist_slot * kHistSlotBytes);
     plan->status   = (uint32_t*)(ws + off_status);
     plan->tmp_keys = (KeyT*)(ws + off_keys);
     plan->tmp_vals = (uint32_t*)(ws + off_vals);
-    // zero histograms + look-back status (contiguous) and the tickets
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ws, 0, off_status + (size_t)info.num_passes * plan->tiles * (1u << rbits) * sizeof(uint32_t), s));
+    // zero this sort's histograms + the look-back status (contiguous) and the tickets
+    char* const zero_from = (char*)plan->hist;
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(zero_from, 0, (size_t)(ws + off_status - zero_from) +
+                                                           (size_t)info.num_passes * plan->tiles * (1u << rbits) * sizeof(uint32_t), s));
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, kMaxSortPasses * sizeof(uint32_t), s));
     return LCGS_B200_OK;
 }
 
+// skip_trivial_last: the last pass returns at once when all its keys have digit 0 (it would be the
+// identity permutation); `alt`, if given, receives that pass's input buffers and its histogram, so that
+// the consumer can make the same test (hist[0] == n) and read the right pair of buffers.
 template <typename KeyT>
 static int launch_sort_t(lcgs_b200_ctx* ctx, const SortPlan<KeyT>& plan, const KeyT* kin, KeyT* kout, const uint32_t* vals_in,
                          uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, uint32_t* ticket,
-                         bool hist_ready, bool record_events, cudaStream_t s)
+                         bool hist_ready, bool record_events, cudaStream_t s, bool skip_trivial_last = false,
+                         SortedPairsU32* alt = nullptr, bool pingpong_with_input = false)
 {
     const size_t bound = plan.bound;
     if (bound == 0) return LCGS_B200_OK;
@@ -585,16 +611,27 @@ static int launch_sort_t(lcgs_b200_ctx* ctx, const SortPlan<KeyT>& plan, const K
                     h[10], h[0] / h[10], h[1] / h[10], h[2] / h[10], h[3] / h[10], h[4] / h[10], h[5] / h[10],
                     (double)h[8] / h[10], (double)h[9] / h[10]);
     }
+    const int ablate = ((g_ablate & kAblateSortStores) ? kSweepAblateStores : 0) | ((g_ablate & kAblateSortLookback) ? kSweepAblateLookback : 0);
     const KeyT*     src_k = kin;
     const uint32_t* src_v = vals_in;
     for (int p = 0; p < info.num_passes; p++) {
-        const bool to_out = ((info.num_passes - 1 - p) % 2) == 0;
-        KeyT*      dst_k  = to_out ? kout : plan.tmp_keys;
-        uint32_t*  dst_v  = to_out ? vals_out : plan.tmp_vals;
+        // default: ping-pong with the workspace so that the last pass lands in (kout, vals_out) and the
+        // input survives; pingpong_with_input: alternate between the output and the (scratch) input
+        // buffers, result in the output buffers for an odd number of passes, else in the input buffers
+        const bool to_out = pingpong_with_input ? (p % 2) == 0 : ((info.num_passes - 1 - p) % 2) == 0;
+        KeyT*      dst_k  = to_out ? kout : (pingpong_with_input ? const_cast<KeyT*>(kin) : plan.tmp_keys);
+        uint32_t*  dst_v  = to_out ? vals_out : (pingpong_with_input ? const_cast<uint32_t*>(vals_in) : plan.tmp_vals);
+        const bool last = p == info.num_passes - 1;
+        if (last && skip_trivial_last && alt) {
+            alt->alt_keys  = reinterpret_cast<const uint32_t*>(src_k);
+            alt->alt_vals  = src_v;
+            alt->last_hist = plan.hist + (size_t)p * radix;
+        }
         var.kernel<<<sweep_blocks, var.threads, var.smem, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
                                                               plan.hist + (size_t)p * radix,
                                                               plan.status + (size_t)p * tiles * radix, ticket + p,
-                                                              info.shift[p], info.mask[p], dbg);
+                                                              info.shift[p], info.mask[p],
+                                                              ((last && skip_trivial_last) ? kSweepSkipIfTrivial : 0) | ablate, dbg);
         LCGS_CUDA_CHECK(ctx, cudaGetLastError());
         src_k = dst_k;
         src_v = dst_v;
@@ -630,19 +667,26 @@ int sort_prepare_u32(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bi
 {
     if (!ctx->plan32) ctx->plan32 = new SortPlan<uint32_t>();
     auto& plan = *static_cast<SortPlan<uint32_t>*>(ctx->plan32);
-    int   rc   = sort_prepare_t<uint32_t>(ctx, bound, begin_bit, end_bit, ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, &plan, s);
+    int   rc   = sort_prepare_t<uint32_t>(ctx, bound, begin_bit, end_bit, ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, &plan, s, 0);
     if (rc) return rc;
     digits->hist = plan.hist; digits->num_passes = plan.info.num_passes; digits->radix_bits = plan.info.radix_bits;
     for (int p = 0; p < kMaxSortPasses; p++) { digits->shift[p] = plan.info.shift[p]; digits->mask[p] = plan.info.mask[p]; }
     return LCGS_B200_OK;
 }
 
-int sort_run_u32(lcgs_b200_ctx* ctx, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
-                 const uint32_t* d_n, size_t capacity, bool hist_ready, cudaStream_t s)
+// Sorts (keys_a, vals_a) using (keys_b, vals_b) as the ping-pong partner; both pairs are scratch.  The
+// result is in res->keys/vals, or in res->alt_* when the last pass skipped itself (SortedPairsU32).
+int sort_run_u32(lcgs_b200_ctx* ctx, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
+                 const uint32_t* d_n, size_t capacity, bool hist_ready, SortedPairsU32* res, cudaStream_t s)
 {
-    const auto& plan = *static_cast<const SortPlan<uint32_t>*>(ctx->plan32);
-    return launch_sort_t<uint32_t>(ctx, plan, keys_in, keys_out, vals_in, vals_out, 0, d_n, capacity,
-                                   ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, hist_ready, false, s);
+    const auto& plan   = *static_cast<const SortPlan<uint32_t>*>(ctx->plan32);
+    const bool  in_b   = (plan.info.num_passes % 2) == 1;  // pass p writes b for even p, a for odd p
+    res->keys = res->alt_keys = in_b ? keys_b : keys_a;
+    res->vals = res->alt_vals = in_b ? vals_b : vals_a;
+    res->last_hist = nullptr;
+    if (plan.info.num_passes == 0) return LCGS_B200_OK;  // nothing to sort by: the input is the result
+    return launch_sort_t<uint32_t>(ctx, plan, keys_a, keys_b, vals_a, vals_b, 0, d_n, capacity,
+                                   ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, hist_ready, false, s, true, res, true);
 }
 
 int sort_prepare_u64(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s)

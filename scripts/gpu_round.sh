@@ -1,7 +1,7 @@
 # usage: bash scripts/gpu_round.sh <tag> [ncu]   -- GPU tests + bench (+ optional ncu launch list)
 TAG=${1:-x}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x --timeout 300 > gpurun_out/pytest_$TAG.log 2>&1; echo pytest rc=$?; tail -12 gpurun_out/pytest_$TAG.log
+timeout 600 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_$TAG.log 2>&1; echo pytest rc=$?; tail -12 gpurun_out/pytest_$TAG.log
 timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo bench rc=$?
 python - <<PY
 import json

@@ -361,3 +361,20 @@ def test_opacity_extremes(lcgs, dev):
     op[2::5] = np.float32(1.0) / np.float32(255.0)
     op[3::5] = 1.0
     _render_and_compare(lcgs, dev, sc, pose, 320, 200, opacity=op, scale_modifier=3.0)
+
+
+def test_far_gaussians_run_the_fourth_depth_pass(lcgs, dev):
+    """The fused frame sorts depth keys relative to bits(0.2f); below depth 13107 they fit three 9-bit
+    digits and the fourth pass skips itself.  Push a third of the Gaussians beyond that depth (scaled
+    up so that they still cover tiles) so the fourth pass has to run, mixed with near ones."""
+    sc, pose = make_case("C3", 6000, 320, 200)
+    pos, scale = sc.pos.copy(), sc.scale.copy()
+    cam = np.asarray(pose[0], np.float32)
+    far = np.arange(pos.shape[0]) % 3 == 0
+    k = np.float32(9000.0)
+    pos[far] = cam + (pos[far] - cam) * k
+    scale[far] = scale[far] * k
+    sc2 = type(sc)(**{**sc.__dict__, "pos": np.ascontiguousarray(pos), "scale": np.ascontiguousarray(scale)})
+    fr = _render_and_compare(lcgs, dev, sc2, pose, 320, 200)
+    touching = fr.tiles_touched > 0
+    assert (fr.depth[touching] > 13200.0).sum() > 100 and (fr.depth[touching] < 100.0).sum() > 100
