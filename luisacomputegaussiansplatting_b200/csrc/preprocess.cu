@@ -72,11 +72,14 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
     float4* const  w_sh = s_sh + warp * 32 * kShRowPad;
 
     // ---- phase 1: geometry ----------------------------------------------------------------
-    float   px = 0.f, py = 0.f, pz = 0.f;
+    float   px = 0.f, py = 0.f, pz = 0.f, op = 0.f;
     Splat2D s;
     s.tiles   = 0;
     bool need = false;
     if (i < a.P) {
+        // opacity is only needed by Gaussians that touch a tile, but a predicated 4-byte load costs a
+        // whole 32-byte sector per Gaussian; unconditionally the warp reads 128 contiguous bytes
+        op = __ldg(a.opacity + i);
         px = __ldg(a.pos + 3 * i);
         py = __ldg(a.pos + 3 * i + 1);
         pz = __ldg(a.pos + 3 * i + 2);
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
             a.color[3 * i + 1] = rgb[1];
             a.color[3 * i + 2] = rgb[2];
         }
-        write_record(a.records + (size_t)i * kRecordFloat4s, s, __ldg(a.opacity + i), rgb);
+        write_record(a.records + (size_t)i * kRecordFloat4s, s, op, rgb);
     }
 }
 

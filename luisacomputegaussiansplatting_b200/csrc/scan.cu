@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(kScanThreads)
 {
     // digit histograms of the depth keys this CTA compacts (the depth sort then skips its histogram kernel)
     __shared__ uint32_t s_hist[4 * 512];
+    // the CTA's compacted (key, index) pairs, staged so that they leave as two coalesced runs
+    __shared__ uint32_t s_key[kCompactTile], s_idx[kCompactTile];
     const bool          do_hist = digits.hist != nullptr && !(ablate & kAblateCompactHist);
     const int           nbins   = do_hist ? (digits.num_passes << digits.radix_bits) : 0;
     for (int k = threadIdx.x; k < nbins; k += kScanThreads) s_hist[k] = 0u;
@@ -151,16 +153,23 @@ __global__ void __launch_bounds__(kScanThreads)
     __syncthreads();
     const uint32_t tile = s_tile;
     if (tile >= num_tiles) return;
-    // blocked arrangement: thread t owns items [base + t*8, +8) -> two 16-byte loads
+    // blocked arrangement: thread t owns items [base + t*8, +8) -> two 16-byte loads per array; the depths
+    // are requested up front for every item (4 B each), not one dependent load per touching Gaussian
     const uint32_t e0 = tile * kCompactTile + tid * kCompactItems;
-    uint32_t       v[kCompactItems];
+    uint32_t       v[kCompactItems], dk[kCompactItems];
     if (e0 + kCompactItems <= n) {
         const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(tiles_touched + e0));
         const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(tiles_touched + e0) + 1);
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(depth + e0));
+        const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(depth + e0) + 1);
         v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+        dk[0] = d0.x; dk[1] = d0.y; dk[2] = d0.z; dk[3] = d0.w; dk[4] = d1.x; dk[5] = d1.y; dk[6] = d1.z; dk[7] = d1.w;
     } else {
 #pragma unroll
-        for (int k = 0; k < kCompactItems; k++) v[k] = (e0 + k < n) ? __ldg(tiles_touched + e0 + k) : 0u;
+        for (int k = 0; k < kCompactItems; k++) {
+            v[k]  = (e0 + k < n) ? __ldg(tiles_touched + e0 + k) : 0u;
+            dk[k] = (e0 + k < n) ? __float_as_uint(__ldg(depth + e0 + k)) : 0u;
+        }
     }
     ScanPair mine{ 0, 0 };
 #pragma unroll
@@ -170,41 +179,47 @@ __global__ void __launch_bounds__(kScanThreads)
     }
     ScanPair       tot;
     const ScanPair excl = block_scan_pair(mine, s_warp, &tot);
-    // two chains (instance sum, touching-Gaussian count), one warp each
+    // two chains (instance sum, touching-Gaussian count), one warp each; the other warps stage meanwhile
     if (tid < 64) {
         const uint32_t pre = (tid < 32) ? lookback_warp_u32(status_sum, tile, tot.a) : lookback_warp_u32(status_cnt, tile, tot.b);
         if ((tid & 31) == 0) s_prefix[tid >> 5] = pre;
     }
-    __syncthreads();
-    uint32_t sum = s_prefix[0] + excl.a, cnt = s_prefix[1] + excl.b;
-    if (tile == num_tiles - 1 && tid == 0) {
-        *d_total = s_prefix[0] + tot.a;
-        *d_count = s_prefix[1] + tot.b;
-    }
+    // stable compaction inside the CTA: slots are handed out in index order
+    uint32_t sum = excl.a, slot = excl.b;
     uint32_t out[kCompactItems];
 #pragma unroll
     for (int k = 0; k < kCompactItems; k++) {
         sum += v[k];
         out[k] = sum;
-        if (v[k] > 0u) {  // stable compaction: slots are handed out in index order
-            const uint32_t key = ((ablate & kAblateCompactDepth) ? (e0 + k) * 2654435761u : __float_as_uint(__ldg(depth + e0 + k))) - kDepthKeyBase;
-            ckeys[cnt] = key;
-            cvals[cnt] = e0 + k;
-            cnt++;
-            if (do_hist) {
-#pragma unroll
-                for (int p = 0; p < 4; p++)
-                    if (p < digits.num_passes) atomicAdd(&s_hist[(p << digits.radix_bits) + ((key >> digits.shift[p]) & digits.mask[p])], 1u);
-            }
+        if (v[k] > 0u) {
+            s_key[slot] = ((ablate & kAblateCompactDepth) ? (e0 + k) * 2654435761u : dk[k]) - kDepthKeyBase;
+            s_idx[slot] = e0 + k;
+            slot++;
         }
     }
+    __syncthreads();
+    const uint32_t base_sum = s_prefix[0], base_cnt = s_prefix[1];
+    if (tile == num_tiles - 1 && tid == 0) {
+        *d_total = base_sum + tot.a;
+        *d_count = base_cnt + tot.b;
+    }
     if (e0 + kCompactItems <= n) {
-        reinterpret_cast<uint4*>(offsets + e0)[0] = make_uint4(out[0], out[1], out[2], out[3]);
-        reinterpret_cast<uint4*>(offsets + e0)[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        reinterpret_cast<uint4*>(offsets + e0)[0] = make_uint4(base_sum + out[0], base_sum + out[1], base_sum + out[2], base_sum + out[3]);
+        reinterpret_cast<uint4*>(offsets + e0)[1] = make_uint4(base_sum + out[4], base_sum + out[5], base_sum + out[6], base_sum + out[7]);
     } else {
 #pragma unroll
         for (int k = 0; k < kCompactItems; k++)
-            if (e0 + k < n) offsets[e0 + k] = out[k];
+            if (e0 + k < n) offsets[e0 + k] = base_sum + out[k];
+    }
+    for (uint32_t i = tid; i < tot.b; i += kScanThreads) {
+        const uint32_t key = s_key[i];
+        ckeys[base_cnt + i] = key;
+        cvals[base_cnt + i] = s_idx[i];
+        if (do_hist) {
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (p < digits.num_passes) atomicAdd(&s_hist[(p << digits.radix_bits) + ((key >> digits.shift[p]) & digits.mask[p])], 1u);
+        }
     }
     if (do_hist) {
         __syncthreads();
@@ -226,7 +241,8 @@ int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const
         LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s));
         return LCGS_B200_OK;
     }
-    LCGS_REQUIRE(ctx, ((((uintptr_t)tiles_touched) | ((uintptr_t)offsets)) & 15) == 0, "scan: tiles_touched / point_offsets must be 16-byte aligned");
+    LCGS_REQUIRE(ctx, ((((uintptr_t)tiles_touched) | ((uintptr_t)offsets) | ((uintptr_t)depth)) & 15) == 0,
+                 "scan: tiles_touched / point_offsets / depth must be 16-byte aligned");
     const uint32_t tiles = (uint32_t)(((size_t)P + kCompactTile - 1) / kCompactTile);
     int            rc    = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * 2 * sizeof(unsigned long long));
     if (rc) return rc;
