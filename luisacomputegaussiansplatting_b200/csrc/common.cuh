@@ -62,7 +62,7 @@ struct lcgs_b200_ctx {
     cudaEvent_t  ev[16];
     int          ev_count   = 0;
     int          ev_valid   = 0;
-    bool         sweep_attr_set[2][24] = {};  // onesweep variants whose shared-memory opt-in has been done
+    bool         sweep_attr_set[2][32] = {};  // onesweep variants whose shared-memory opt-in has been done
     void*        plan32 = nullptr;   // prepared sorts of the fused path (sort.cu)
     void*        plan64 = nullptr;
     cudaEvent_t  ev_sort[3] = { nullptr, nullptr, nullptr };  // before histogram, before passes, after passes

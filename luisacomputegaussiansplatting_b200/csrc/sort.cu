@@ -41,6 +41,13 @@ __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v)
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ uint32_t atom_shared_add(uint32_t addr, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ size_t resolve_n(size_t n_host, const uint32_t* d_n, size_t capacity)
 {
     if (!d_n) return n_host;
@@ -141,9 +148,16 @@ __device__ __forceinline__ unsigned digit_peers(uint32_t d)
     unsigned peers = 0xFFFFFFFFu;
 #pragma unroll
     for (int b = 0; b < BITS; b++) {
-        const bool     bit = (d >> b) & 1u;
-        const unsigned m   = __ballot_sync(0xFFFFFFFFu, bit);
-        peers &= bit ? m : ~m;
+        // peers &= ballot(bit b set) ^ (bit b set ? 0 : ~0), spelled out so that it stays four instructions
+        // (test, vote, select, lop3); nvcc otherwise shifts, tests twice and selects per bit
+        asm volatile(
+            "{\n .reg .pred p;\n .reg .b32 m, s;\n"
+            " and.b32 s, %1, %2;\n setp.ne.u32 p, s, 0;\n"
+            " vote.sync.ballot.b32 m, p, 0xffffffff;\n"
+            " selp.b32 s, 0, 0xffffffff, p;\n"
+            " lop3.b32 %0, %0, m, s, 0x60;\n}"
+            : "+r"(peers)
+            : "r"(d), "r"(1u << b));
     }
     return peers;
 }
@@ -179,6 +193,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const bool     is_digit  = tid < RADIX;
     const bool     hi_word   = shift >= 32;  // uniform: the digit lives entirely in the key's high word
     uint32_t* const my_hist  = s_wh + warp * RADIX;
+    const uint32_t  my_hist_addr = (uint32_t)__cvta_generic_to_shared(my_hist);
     // every key has digit 0 in this pass (the top bits of the depth keys): the pass is the identity
     // permutation; the consumers of the sorted list make the same test and read this pass's input
     if ((flags & kSweepSkipIfTrivial) && __ldg(hist) == (uint32_t)n) return;
@@ -245,7 +260,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             const unsigned peers  = full ? digit_peers<RBITS, USE_MATCH>(d) : digit_peers<RBITS + 1, USE_MATCH>(d);
             const unsigned lower  = peers & lt_mask;
             uint32_t       before = 0;
-            if (valid && lower == 0u) before = atomicAdd(&my_hist[d], (uint32_t)__popc(peers));
+            if (valid && lower == 0u) before = atom_shared_add(my_hist_addr + d * 4u, (uint32_t)__popc(peers));
             before = __shfl_sync(0xFFFFFFFFu, before, __ffs(peers) - 1);
             rd[j]  = (d << 16) | (before + __popc(lower));
         }
@@ -423,6 +438,10 @@ static const SweepVariant<unsigned long long> kSweep64[] = {
     LCGS_SWEEP(unsigned long long, 256, 8, 7, 6, false),  // 20
     LCGS_SWEEP(unsigned long long, 128, 16, 7, 8, false), // 21
     LCGS_SWEEP(unsigned long long, 256, 20, 7, 2, false), // 22
+    LCGS_SWEEP(unsigned long long, 256, 24, 7, 2, false), // 23
+    LCGS_SWEEP(unsigned long long, 384, 16, 7, 2, false), // 24
+    LCGS_SWEEP(unsigned long long, 256, 28, 7, 2, false), // 25
+    LCGS_SWEEP(unsigned long long, 128, 32, 7, 4, false), // 26
 };
 // 32-bit depth keys of the per-Gaussian sort
 static const SweepVariant<uint32_t> kSweep32[] = {
@@ -436,6 +455,8 @@ static const SweepVariant<uint32_t> kSweep32[] = {
     LCGS_SWEEP(uint32_t, 512, 4, 9, 4, false),  // 7
     LCGS_SWEEP(uint32_t, 512, 12, 9, 2, false), // 8
     LCGS_SWEEP(uint32_t, 512, 16, 9, 1, false), // 9
+    LCGS_SWEEP(uint32_t, 512, 24, 9, 1, false), // 10
+    LCGS_SWEEP(uint32_t, 1024, 8, 9, 1, false), // 11
 };
 constexpr int kMinSweepTile = 2048;
 constexpr size_t kHistSlotBytes = (size_t)kMaxSortPasses * kMaxRadix * sizeof(uint32_t);  // 16 KB, 256-byte multiple
@@ -467,7 +488,7 @@ static int sweep_variant_index(int bits)
         if (e && atoi(e) >= 0 && atoi(e) < SweepTable<KeyT>::count()) env_idx = atoi(e);
     }
     if (env_idx >= 0) return env_idx;
-    if (sizeof(KeyT) == 8) return bits <= 14 ? 19 : 0;  // 7-bit tile digits, 256 x 12, 4 CTAs/SM, ballots | 9-bit, MATCH
+    if (sizeof(KeyT) == 8) return bits <= 14 ? 22 : 0;  // 7-bit tile digits, 256 x 20, 2 CTAs/SM, ballots | 9-bit, MATCH
     return 9;                                            // depth keys: 9-bit digits, one 8192-pair tile per SM
 }
 
