@@ -231,33 +231,32 @@ __global__ void __launch_bounds__(kEmitThreads)
                 const uint32_t o_magic = __shfl_sync(FULL, magic, l);
                 const uint32_t o_dbits = __shfl_sync(FULL, dbits[c], l);
                 const uint32_t o_idx   = __shfl_sync(FULL, idx[c], l);
-                if (p < total) {
-                    const uint32_t j    = p - o_loc;
-                    const uint32_t ry   = exact_div ? (o_w == 1u ? j : __umulhi(j, o_magic)) : j / o_w;  // magic wraps for w == 1
-                    const uint32_t rx   = j - ry * o_w;
-                    const uint32_t tile = ((o_xy0 & 0xFFFFu) + rx) + ((o_xy0 >> 16) + ry - row0) * gx;
-                    const size_t   dst  = (size_t)excl0 + p;
-                    if (dst < capacity) {
-                        if (!(ablate & kAblateDupStores)) {
-                            keys[dst] = ((unsigned long long)tile << 32) | (unsigned long long)o_dbits;
-                            vals[dst] = o_idx;
-                        }
-                        if (do_hist) {
-                            red_shared_add(hist_addr + (((tile >> sh0) & m0) << 2), 1u);
-                            if (two_digits) {
-                                // the active lanes are a prefix of the warp and emit consecutive tiles: runs
-                                // of equal upper digits are counted by their first lane (MATCH.ANY is slow)
-                                const uint32_t d1      = (tile >> sh1) & m1;
-                                const unsigned act     = __activemask();
-                                const uint32_t prev    = __shfl_up_sync(act, d1, 1);
-                                const bool     lead    = lane == 0 || prev != d1;
-                                const unsigned leaders = __ballot_sync(act, lead);
-                                if (lead) {
-                                    const unsigned above = leaders & ~le_mask;
-                                    const int      end   = above ? __ffs(above) - 1 : __popc(act);
-                                    red_shared_add(hist1_addr + (d1 << 2), (uint32_t)(end - lane));
-                                }
-                            }
+                // every lane computes (sync intrinsics below stay convergent with the full mask); lanes past the
+                // end of the run or of the list capacity -- a suffix of the warp -- neither store nor count
+                const uint32_t j    = p - o_loc;
+                const uint32_t ry   = exact_div ? (o_w == 1u ? j : __umulhi(j, o_magic)) : j / o_w;  // magic wraps for w == 1
+                const uint32_t rx   = j - ry * o_w;
+                const uint32_t tile = ((o_xy0 & 0xFFFFu) + rx) + ((o_xy0 >> 16) + ry - row0) * gx;
+                const size_t   dst  = (size_t)excl0 + p;
+                const bool     emit = p < total && dst < capacity;
+                if (emit && !(ablate & kAblateDupStores)) {
+                    keys[dst] = ((unsigned long long)tile << 32) | (unsigned long long)o_dbits;
+                    vals[dst] = o_idx;
+                }
+                if (do_hist) {
+                    if (emit) red_shared_add(hist_addr + (((tile >> sh0) & m0) << 2), 1u);
+                    if (two_digits) {
+                        // consecutive lanes emit consecutive tiles: runs of equal upper digits are counted by
+                        // their first lane (MATCH.ANY is slow)
+                        const uint32_t d1      = (tile >> sh1) & m1;
+                        const uint32_t prev    = __shfl_up_sync(FULL, d1, 1);
+                        const bool     lead    = emit && (lane == 0 || prev != d1);
+                        const unsigned leaders = __ballot_sync(FULL, lead);
+                        const int      n_emit  = __popc(__ballot_sync(FULL, emit));
+                        if (lead) {
+                            const unsigned above = leaders & ~le_mask;
+                            const int      end   = above ? __ffs(above) - 1 : n_emit;
+                            red_shared_add(hist1_addr + (d1 << 2), (uint32_t)(end - lane));
                         }
                     }
                 }
