@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
     if (d_num_rendered && *d_num_rendered == 0u) return;
 
     // [buffer][plane][slot]: plane 0 = (pix.x, pix.y, -0.5*conic.x, -conic.y),
-    // plane 1 = (-0.5*conic.z, threshold, opacity, ry), plane 2 = (r, g, b, rx)
+    // plane 1 = (-0.5*conic.z, threshold, log2(opacity), ry), plane 2 = (r, g, b, rx)
     __shared__ float4   s_rec[2][3][kBlendThreads];
     __shared__ uint32_t s_cnt[2][kBlendWarps];
 
@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
         const bool     keep = valid && !cull_rect_fast(a.x, a.y, a.z, a.w, b.x, b.y, b.w, c.w, tx0, ty0, tx1, ty1);
         const unsigned kept = __ballot_sync(FULL, keep);
         if (keep) {
-            const uint32_t slot = warp * 32 + __popc(kept & lt_mask);
+            // a warp's survivors fill its segment from the top, earliest candidate in slot 31: the consumer
+            // then walks the hit mask from its highest bit, which is a single FLO (no bit reversal)
+            const uint32_t slot = warp * 32 + 31 - __popc(kept & lt_mask);
             const uint32_t addr = sbase + buf * kBuf + slot * 16u;
             sts128(addr, a);
             sts128(addr + kPlane, b);
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
                 const uint32_t cnt     = s_cnt[buf][seg];
                 const uint32_t segbase = abase + seg * 512u;
                 bool           hit     = false;
-                if ((uint32_t)lane < cnt) {
+                if ((uint32_t)lane + cnt >= 32u) {
                     const float4 ga = lds128(segbase + lane * 16u);
                     const float4 gb = lds128(segbase + kPlane + lane * 16u);
                     const float  rx = lds32(segbase + 2u * kPlane + lane * 16u + 12u);
@@ -164,8 +166,9 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
                 }
                 unsigned hits = __ballot_sync(FULL, hit);
                 while (hits) {
-                    const uint32_t addr = segbase + (__ffs(hits) - 1) * 16u;
-                    hits &= hits - 1u;
+                    const int      top  = 31 - __clz(hits);
+                    const uint32_t addr = segbase + top * 16u;
+                    hits ^= 1u << top;
                     const float4 ea = lds128(addr);
                     const float4 eb = lds128(addr + kPlane);
                     const float4 ec = lds128(addr + 2u * kPlane);
@@ -173,7 +176,8 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
                     const float power = blend_power(ea.z, ea.w, eb.x, ea.x - pxf, ea.y - pyf);
                     // shader.cpp:257,259: skipped pairs are predicated off
                     const bool  ok     = !(power > 0.0f) && !(power < eb.y);
-                    const float alpha  = fminf(0.99f, eb.z * ex2_ftz(power * 1.4426950408889634f));
+                    // opacity * exp(power) = 2^(power * log2(e) + log2(opacity)): one FMA in front of MUFU.EX2
+                    const float alpha  = fminf(0.99f, ex2_ftz(__fmaf_rn(power, 1.4426950408889634f, eb.z)));
                     const float test_T = T * (1.0f - alpha);         // < 0 for a finished pixel
                     const bool  blend  = ok && !(test_T < 0.0001f);  // shader.cpp:261-265
                     const float w      = blend ? T * alpha : 0.0f;

@@ -14,7 +14,7 @@ constexpr int kNumSMs = 148;  // B200; the real count is queried at ctx creation
 
 // Per-Gaussian record the blend kernel gathers: three float4 (48 B, two 32-B sectors).
 //   r0 = (pix.x, pix.y, -0.5*conic.x, -conic.y)
-//   r1 = (-0.5*conic.z, power threshold of the alpha test, opacity, cull quotient ry or NaN)
+//   r1 = (-0.5*conic.z, power threshold of the alpha test, log2(opacity), cull quotient ry or NaN)
 //   r2 = (red, green, blue, cull quotient rx)            -- see cull_coef() in lcgs_math.cuh
 constexpr int kRecordFloat4s = 3;
 

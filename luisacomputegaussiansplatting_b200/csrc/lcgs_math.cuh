@@ -343,7 +343,8 @@ LCGS_HD bool alpha_passes(float op, float power)
 // Smallest power <= 0 for which the alpha test passes; +inf if none (opacity < 1/255).
 LCGS_HD float alpha_threshold(float op)
 {
-    if (!alpha_passes(op, 0.0f)) return INFINITY;
+    // power 0: exp_rn(0) == 1 exactly, so the test is on min(0.99, opacity) itself
+    if (fminf(0.99f, op) < 1.0f / 255.0f) return INFINITY;
     if (!(op <= 3.0e38f)) return -INFINITY;  // inf / NaN opacity: every power passes
     // bits of non-positive floats grow as the value decreases: 0x80000000 (-0) .. 0xFF800000 (-inf)
     const uint32_t U_ZERO = 0x80000000u, U_NINF = 0xFF800000u;

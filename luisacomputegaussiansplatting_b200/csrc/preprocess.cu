@@ -55,7 +55,7 @@ __device__ __forceinline__ void write_record(float4* rec, const Splat2D& s, floa
     const float    a = -0.5f * s.conic[0], b = -s.conic[1], c = -0.5f * s.conic[2];
     const CullCoef k = cull_coef(s.px, s.py, a, b, c, thr);
     rec[0] = make_float4(s.px, s.py, a, b);
-    rec[1] = make_float4(c, thr, op, k.ry);
+    rec[1] = make_float4(c, thr, log2f(op), k.ry);  // the blend evaluates alpha as 2^(power*log2e + log2(opacity))
     rec[2] = make_float4(rgb[0], rgb[1], rgb[2], k.rx);
 }
 
