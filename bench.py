@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--gaussians", type=int, default=None, help="override P (debugging only; invalidates the number)")
     ap.add_argument("--orbit", action="store_true", help="rank r / step s renders orbit view s*N+r instead of the fixed pose")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how finished frames reach rank 0 -- peer: every rank's blend kernel stores straight into "
+                         "rank 0's peer-mapped ring over NVLink (the gather is fused into the render); nccl: dist.gather")
     ap.add_argument("--capacity", type=int, default=None,
                     help="instance list capacity L (default 20 000 000 = app/main.cpp:245; 260 000 000 for C5)")
     args = ap.parse_args()
@@ -76,7 +79,9 @@ def workload_config(args, cfg, P, extra=None):
          "gaussians": P, "width": cfg.W, "height": cfg.H, "sh_degree": 3,
          "l2": "inputs (%.2f GB Gaussian set + %.2f GB instance lists) exceed the 126 MB L2; no explicit flush" % (
              P * 236 / 1e9, args.capacity * 24 / 1e9),
-         "parallelism": "view-sharded x%d (scene replicated, NCCL frame gather to rank 0)" % args.gpus if args.gpus > 1
+         "parallelism": ("view-sharded x%d (scene replicated, %s)" % (
+             args.gpus, "frames blended straight into rank 0's peer-mapped ring over NVLink" if args.gather == "peer"
+             else "NCCL frame gather to rank 0")) if args.gpus > 1
          else "single GPU"}
     if extra:
         c.update(extra)
@@ -202,9 +207,9 @@ class ClockSampler:
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 
-# preprocess, scan+compact (+depth histograms), [depth sort: 4 passes], gather scan, duplicate_keys (+tile histograms), [tile sort: 2 passes],
-# ranges, blend
-KERNELS_PER_FRAME = 12
+# preprocess, scan+compact (+depth histograms), [depth sort: 4 passes, the last one returns at once], duplicate_keys
+# (+chained offsets, tile histograms), [tile sort: 2 passes], ranges, blend
+KERNELS_PER_FRAME = 11
 
 
 def run_b200(args):
@@ -238,17 +243,27 @@ def run_b200(args):
             return scenes.orbit_pose(step * world + rank)
         return scenes.CAM_POS, scenes.CAM_TARGET, scenes.world_up(cfg.world)
 
-    # N > 1: frames are rendered into two alternating device images so that the NCCL gather of frame i
-    # (to rank 0) overlaps the render of frame i+1
+    # N > 1, --gather peer (default): rank 0 owns a ring of 2 x N frames every rank can write over NVLink;
+    # rank r blends frame i straight into slot (i & 1) * N + r, so the gather IS the blend's stores.
+    # --gather nccl: frames are rendered into two alternating device images so that the NCCL gather of
+    # frame i (to rank 0) overlaps the render of frame i+1.
+    use_peer = world > 1 and args.gather == "peer"
+    ring = None
+    if use_peer:
+        from luisacomputegaussiansplatting_b200 import distributed as D
+        ring = D.PeerFrameRing(dev, W, H, slots=2 * world)
     frame_imgs = [r.img, torch.empty_like(r.img)] if world > 1 else [r.img]
     gather_lists = [None, None]
-    if world > 1 and rank == 0:
+    if world > 1 and rank == 0 and not use_peer:
         gather_lists = [[torch.empty_like(r.img) for _ in range(world)] for _ in range(2)]
     pending = [None, None]
 
     def step_device(i):
         cam = lcgs.make_camera(*pose(i), W, H)
-        if world > 1:
+        if use_peer:
+            r.set_target_ptr(ring.ptr((i & 1) * world + rank))
+            r.render_async(lcgs.view_params(cam))
+        elif world > 1:
             b = i & 1
             if pending[b] is not None:
                 pending[b].wait()                      # buffer b has been sent: the stream may overwrite it
@@ -372,6 +387,8 @@ def run_b200(args):
                     "steps": k}
         del pinned
 
+    if ring is not None:
+        ring.close()  # the owner frees, the others unmap (after a device sync)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -251,6 +251,24 @@ LCGS_B200_API int lcgs_b200_stage_times(lcgs_b200_ctx* ctx, float ms[LCGS_B200_N
  * `num_passes` onesweep launches (passes_ms / num_passes = average launch duration). */
 LCGS_B200_API int lcgs_b200_sort_breakdown(lcgs_b200_ctx* ctx, float* histogram_ms, float* passes_ms, int* num_passes);
 
+/* ---- multi-GPU: peer-writable output buffers (no reference counterpart: the reference drives one device,
+ * app/main.cpp:162-163) ----
+ *
+ * One process per GPU.  The rank that assembles the result owns a device buffer every other rank can
+ * WRITE with plain stores over NVLink (CUDA IPC + peer access): a rank passes the opened pointer (plus the
+ * byte offset of its slot) as `target_img`, and the blend kernel's image stores are the transfer -- the
+ * gather of finished frames / tile-row strips needs no separate collective or staging copy.  The owner
+ * may read a slot after the writer's stream has finished its frame and the ranks have met at a barrier. */
+#define LCGS_B200_PEER_HANDLE_BYTES 64
+/* Owner: allocate `bytes` of zeroed device memory and export its interprocess handle. */
+LCGS_B200_API int lcgs_b200_peer_alloc(lcgs_b200_ctx* ctx, size_t bytes, void** dev_ptr,
+                                       unsigned char handle[LCGS_B200_PEER_HANDLE_BYTES]);
+/* Other ranks (other processes, other GPUs of the node): map the owner's buffer; enables peer access. */
+LCGS_B200_API int lcgs_b200_peer_open(lcgs_b200_ctx* ctx, const unsigned char handle[LCGS_B200_PEER_HANDLE_BYTES],
+                                      void** dev_ptr);
+LCGS_B200_API int lcgs_b200_peer_close(lcgs_b200_ctx* ctx, void* dev_ptr); /* unmap (other ranks) */
+LCGS_B200_API int lcgs_b200_peer_free(lcgs_b200_ctx* ctx, void* dev_ptr);  /* free (owner) */
+
 /* ---- tuning hook (no reference counterpart) ---- */
 
 /* Makes kernels DROP parts of their work (bit mask, see kAblate* in csrc/common.cuh) so that the cost of

@@ -53,6 +53,7 @@ class Frame(C.Structure):
                 ("radii", C.c_void_p), ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int)]
 
 
+PEER_HANDLE_BYTES = 64
 _VP = C.c_void_p
 _I = C.c_int
 _F = C.c_float
@@ -91,6 +92,10 @@ _PROTOS = {
     "lcgs_b200_set_profiling": (_I, [_VP, _I]),
     "lcgs_b200_stage_times": (_I, [_VP, C.POINTER(_F)]),
     "lcgs_b200_sort_breakdown": (_I, [_VP, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I)]),
+    "lcgs_b200_peer_alloc": (_I, [_VP, _SZ, C.POINTER(_VP), C.c_char_p]),
+    "lcgs_b200_peer_open": (_I, [_VP, C.c_char_p, C.POINTER(_VP)]),
+    "lcgs_b200_peer_close": (_I, [_VP, _VP]),
+    "lcgs_b200_peer_free": (_I, [_VP, _VP]),
     "lcgs_b200_debug_ablate": (None, [_I]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)

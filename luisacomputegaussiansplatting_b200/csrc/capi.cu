@@ -562,6 +562,54 @@ int lcgs_b200_read_image(lcgs_b200_ctx* ctx, const lcgs_b200_frame* fr, float* h
     return LCGS_B200_OK;
 }
 
+// ---- multi-GPU: peer-writable output buffers (CUDA IPC) ---------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == LCGS_B200_PEER_HANDLE_BYTES, "IPC handle size");
+
+int lcgs_b200_peer_alloc(lcgs_b200_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char handle[LCGS_B200_PEER_HANDLE_BYTES])
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, dev_ptr && handle && bytes > 0, "peer_alloc: bad argument");
+    void* p = nullptr;
+    LCGS_CUDA_CHECK(ctx, cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+        snprintf(ctx->last_error, sizeof(ctx->last_error), "peer_alloc: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(p);
+        return LCGS_B200_ERR_CUDA;
+    }
+    memcpy(handle, &h, sizeof(h));
+    *dev_ptr = p;
+    return LCGS_B200_OK;
+}
+
+int lcgs_b200_peer_open(lcgs_b200_ctx* ctx, const unsigned char handle[LCGS_B200_PEER_HANDLE_BYTES], void** dev_ptr)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, dev_ptr && handle, "peer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    LCGS_CUDA_CHECK(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return LCGS_B200_OK;
+}
+
+int lcgs_b200_peer_close(lcgs_b200_ctx* ctx, void* dev_ptr)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_CUDA_CHECK(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    return LCGS_B200_OK;
+}
+
+int lcgs_b200_peer_free(lcgs_b200_ctx* ctx, void* dev_ptr)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_CUDA_CHECK(ctx, cudaFree(dev_ptr));
+    return LCGS_B200_OK;
+}
+
 int lcgs_b200_set_profiling(lcgs_b200_ctx* ctx, int enabled)
 {
     int rc = enter(ctx);

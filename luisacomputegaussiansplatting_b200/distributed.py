@@ -107,6 +107,82 @@ def gather_strips(img: torch.Tensor, bands: Sequence[Tuple[int, int]], height: i
 
 
 # --------------------------------------------------------------------------------------------------
+# the exchange fused into the render: peer stores instead of a collective
+# --------------------------------------------------------------------------------------------------
+
+class PeerFrameRing:
+    """`slots` planar [3,H,W] float32 images in ONE buffer on rank `dst` that every rank can write over
+    NVLink (lcgs.PeerBuffer).  A rank renders straight into `ptr(slot)` -- or, for tile-row sharding, all
+    ranks render their bands into the same slot -- so the blend kernel's stores are the gather.  After the
+    writers' streams have finished and the ranks have met at a barrier, dst reads the frames."""
+
+    def __init__(self, device, width: int, height: int, slots: int, dst: int = 0, group=None):
+        from . import lcgs
+
+        self.W, self.H, self.slots, self.dst, self.group = width, height, slots, dst, group
+        self.frame_bytes = 3 * width * height * 4
+        self.buf = lcgs.PeerBuffer(device, self.frame_bytes * slots, owner=dst, group=group)
+
+    def ptr(self, slot: int) -> int:
+        assert 0 <= slot < self.slots
+        return self.buf.ptr + slot * self.frame_bytes
+
+    def complete(self):
+        """All frames enqueued so far (on every rank) are visible on dst when this returns."""
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def frame(self, slot: int):
+        """dst only: host copy of a slot as [3, H, W] float32."""
+        return self.buf.to_host(slot * self.frame_bytes, 3 * self.W * self.H).reshape(3, self.H, self.W)
+
+    def release(self):
+        """dst has read what it wanted: the writers may reuse the slots when this returns (collective)."""
+        dist.barrier(group=self.group)
+
+    def close(self):
+        """Collective: the writers unmap, then the owner frees."""
+        if not self.buf.is_owner:
+            self.buf.close()
+        dist.barrier(group=self.group)
+        if self.buf.is_owner:
+            self.buf.close()
+
+
+def render_sweep_view_sharded_peer(render_view_into: Callable[[int, int], None], num_views: int, ring: PeerFrameRing):
+    """View sharding with the gather fused into the render: view k is rendered by rank k mod G directly
+    into slot k of `ring` (ring.slots >= num_views) on the destination rank.  `render_view_into(k, ptr)`
+    enqueues the frame of view k with target pointer `ptr`.  Returns the frames (host arrays) on dst."""
+    world = dist.get_world_size(ring.group)
+    rank = dist.get_rank(ring.group)
+    assert ring.slots >= num_views
+    for k in shard_views(num_views, world, rank):
+        render_view_into(k, ring.ptr(k))
+    ring.complete()
+    frames = [ring.frame(k) for k in range(num_views)] if rank == ring.dst else None
+    ring.release()
+    return frames
+
+
+def render_frame_tile_row_sharded_peer(render_band_into: Callable[[int, int, int], None], height: int, ring: PeerFrameRing,
+                                       slot: int = 0, weights: Optional[Sequence[float]] = None):
+    """Tile-row sharding with the gather fused into the render: every rank renders its band of tile rows
+    directly into the SAME image (slot `slot` of `ring`) on the destination rank.
+    `render_band_into(r0, r1, ptr)` enqueues the band [r0, r1) with target pointer `ptr`.
+    Returns (assembled host image on dst / None, bands)."""
+    world = dist.get_world_size(ring.group)
+    rank = dist.get_rank(ring.group)
+    bands = split_tile_rows((height + 15) // 16, world, weights)
+    r0, r1 = bands[rank]
+    if r1 > r0:
+        render_band_into(r0, r1, ring.ptr(slot))
+    ring.complete()
+    img = ring.frame(slot) if rank == ring.dst else None
+    ring.release()
+    return img, bands
+
+
+# --------------------------------------------------------------------------------------------------
 # drivers
 # --------------------------------------------------------------------------------------------------
 

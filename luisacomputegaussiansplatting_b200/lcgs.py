@@ -346,6 +346,47 @@ class GSTileSplatter:
 # fused frame renderer (what the app's loop does, app/main.cpp:266-308)
 # --------------------------------------------------------------------------------------------------
 
+class PeerBuffer:
+    """Device memory on the `owner` rank that every rank of the process group can write with plain stores
+    over NVLink (lcgs_b200_peer_alloc / _open: CUDA IPC + peer access).  Passed as a render target, the
+    blend kernel's image stores are the transfer: finished frames / tile-row strips land on the owner
+    without a separate collective.  `ptr` is valid in the calling process only."""
+
+    def __init__(self, device: Device, nbytes: int, owner: int = 0, group=None):
+        import torch.distributed as dist
+
+        self.device, self.nbytes, self.owner = device, int(nbytes), owner
+        self.rank = dist.get_rank(group)
+        self.is_owner = self.rank == owner
+        p = C.c_void_p()
+        handle = C.create_string_buffer(_capi.PEER_HANDLE_BYTES)
+        if self.is_owner:
+            device.check(device.lib.lcgs_b200_peer_alloc(device.ctx, self.nbytes, C.byref(p), handle))
+        box = [handle.raw if self.is_owner else None]
+        dist.broadcast_object_list(box, src=owner, group=group)
+        if not self.is_owner:
+            device.check(device.lib.lcgs_b200_peer_open(device.ctx, box[0], C.byref(p)))
+        self.ptr = int(p.value)
+
+    def to_host(self, offset_bytes: int, count: int) -> np.ndarray:
+        """float32 view of [offset, offset + 4*count) copied to the host (synchronises the device)."""
+        out = torch.empty(count, dtype=torch.float32).pin_memory()
+        torch.cuda.synchronize()
+        from cuda.bindings import runtime as cudart  # host copy from raw device memory
+
+        err, = cudart.cudaMemcpy(out.data_ptr(), self.ptr + offset_bytes, 4 * count, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+        if int(err) != 0:
+            raise RuntimeError("cudaMemcpy from peer buffer failed: %s" % err)
+        return out.numpy().copy()
+
+    def close(self):
+        if self.ptr:
+            d = self.device
+            torch.cuda.synchronize()
+            d.check((d.lib.lcgs_b200_peer_free if self.is_owner else d.lib.lcgs_b200_peer_close)(d.ctx, C.c_void_p(self.ptr)))
+            self.ptr = 0
+
+
 class Renderer:
     """Device-resident scene + frame buffers + the fused lcgs_b200_render call."""
 
@@ -425,6 +466,11 @@ class Renderer:
         assert img.numel() == 3 * self.W * self.H and img.dtype == torch.float32
         self.img = img
         self.c_frame.target_img = _ptr(img)
+
+    def set_target_ptr(self, ptr: int):
+        """Render the following frames into raw device memory (e.g. a slot of a PeerBuffer on another GPU):
+        a planar [3*H*W] float32 image at `ptr`.  `image()` keeps referring to the local buffer."""
+        self.c_frame.target_img = C.c_void_p(int(ptr))
 
     def read_num_rendered_async(self, host_count: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
         """Enqueue a copy of the last enqueued frame's num_rendered into a pinned int32 host tensor."""

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Multi-GPU check over NCCL (run under torchrun): view-sharded sweep and tile-row-sharded frame must
-reproduce single-GPU frames bit for bit.
+"""Multi-GPU check (run under torchrun): view-sharded sweep and tile-row-sharded frame must reproduce
+single-GPU frames bit for bit -- gathered over NCCL, and with the gather fused into the render (every rank's
+blend kernel stores straight into rank 0's peer-mapped buffer over NVLink).
 
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/multi_gpu_check.py [--config C3 --gaussians 400000]
 """
@@ -52,6 +53,26 @@ if rank == 0:
         ok &= bool(torch.equal(frames[k].view(torch.int32), want.view(torch.int32)))
     out["view_sharded_bit_exact"] = ok
 
+# ---- the same sweep with the gather fused into the render: peer stores into rank 0's ring ---------------
+ring = D.PeerFrameRing(dev, W, H, slots=args.views)
+
+
+def render_view_into(k, ptr):
+    r.set_target_ptr(ptr)
+    r.render_async(lcgs.view_params(lcgs.make_camera(*scenes.orbit_pose(k * 16), W, H)))
+
+
+torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+frames_p = D.render_sweep_view_sharded_peer(render_view_into, args.views, ring)
+out["sweep_peer_s"] = time.perf_counter() - t0
+r.set_target(r.img)
+if rank == 0:
+    ok = True
+    for k in range(args.views):
+        want = render_view(k).cpu().numpy()
+        ok &= bool(np.array_equal(frames_p[k].view(np.uint32), want.view(np.uint32)))
+    out["view_sharded_peer_bit_exact"] = ok
+
 # ---- tile-row sharding: one frame split into bands balanced by instance count ------------------------
 pose = (scenes.CAM_POS, scenes.CAM_TARGET, scenes.world_up(cfg.world))
 cam = lcgs.make_camera(*pose, W, H)
@@ -66,6 +87,19 @@ rb = lcgs.Renderer(dev, sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, W, H, list
 n_band = torch.tensor([rb.render(cam) if r1 > r0 else 0], device="cuda", dtype=torch.int64)
 img, _ = D.render_frame_tile_row_sharded(lambda a, b: rb.image(), H, weights)
 dist.all_reduce(n_band)
+# the same frame with every band blended straight into ONE image on rank 0 (peer stores)
+vp = lcgs.view_params(cam)
+
+
+def render_band_into(a, b, ptr):
+    rb.set_target_ptr(ptr)
+    rb.render_async(vp)
+
+
+img_p, _ = D.render_frame_tile_row_sharded_peer(render_band_into, H, ring, slot=0, weights=weights)
+if rank == 0:
+    out["tile_row_sharded_peer_bit_exact"] = bool(np.array_equal(img_p.view(np.uint32), full_img.cpu().numpy().view(np.uint32)))
+ring.close()
 if rank == 0:
     out["bands"] = bands
     out["instances_partition_exactly"] = int(n_band.item()) == n_full
@@ -73,4 +107,5 @@ if rank == 0:
     out["num_rendered"] = n_full
     print(json.dumps(out), flush=True)
     assert out["view_sharded_bit_exact"] and out["tile_row_sharded_bit_exact"] and out["instances_partition_exactly"]
+    assert out["view_sharded_peer_bit_exact"] and out["tile_row_sharded_peer_bit_exact"]
 dist.destroy_process_group()
