@@ -251,7 +251,17 @@ def run_b200(args):
     ring = None
     if use_peer:
         from luisacomputegaussiansplatting_b200 import distributed as D
-        ring = D.PeerFrameRing(dev, W, H, slots=2 * world)
+        ok = torch.ones(1, device="cuda")
+        try:
+            ring = D.PeerFrameRing(dev, W, H, slots=2 * world)
+        except Exception as e:  # e.g. no peer access between two GPUs of the box: every rank falls back together
+            sys.stderr.write("rank %d: peer ring unavailable (%s); falling back to the NCCL gather\n" % (rank, e))
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            if ring is not None:
+                ring.buf.close()
+            ring, use_peer, args.gather = None, False, "nccl"
     frame_imgs = [r.img, torch.empty_like(r.img)] if world > 1 else [r.img]
     gather_lists = [None, None]
     if world > 1 and rank == 0 and not use_peer:
