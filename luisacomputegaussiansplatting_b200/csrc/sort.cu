@@ -488,7 +488,10 @@ static int sweep_variant_index(int bits)
         if (e && atoi(e) >= 0 && atoi(e) < SweepTable<KeyT>::count()) env_idx = atoi(e);
     }
     if (env_idx >= 0) return env_idx;
-    if (sizeof(KeyT) == 8) return bits <= 14 ? 22 : 0;  // 7-bit tile digits, 256 x 20, 2 CTAs/SM, ballots | 9-bit, MATCH
+    // measured: two 7-bit ballot passes for up to 14 tile bits (256 x 20, 2 CTAs/SM); two 9-bit ballot passes up to
+    // 18 bits (the 8K frame's 17 tile bits: 4.8 ms vs 5.4 ms with MATCH); MATCH ranking for longer keys
+    // (the reference flow's 45 bits = 5 passes: 1.11 ms vs 1.17 ms with ten ballots per item)
+    if (sizeof(KeyT) == 8) return bits <= 14 ? 22 : (bits <= 18 ? 17 : 0);
     return 9;                                            // depth keys: 9-bit digits, one 8192-pair tile per SM
 }
 
