@@ -15,6 +15,8 @@
 // HBM-bound: algorithmic bytes = 8*n (histogram) + 24*n per pass.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace lcgs_b200 {
@@ -148,21 +150,30 @@ __device__ __forceinline__ unsigned digit_peers(uint32_t d)
     unsigned peers = 0xFFFFFFFFu;
 #pragma unroll
     for (int b = 0; b < BITS; b++) {
-        // peers &= ballot(bit b set) ^ (bit b set ? 0 : ~0), spelled out so that it stays four instructions
-        // (test, vote, select, lop3); nvcc otherwise shifts, tests twice and selects per bit
-        asm volatile(
-            "{\n .reg .pred p;\n .reg .b32 m, s;\n"
-            " and.b32 s, %1, %2;\n setp.ne.u32 p, s, 0;\n"
-            " vote.sync.ballot.b32 m, p, 0xffffffff;\n"
-            " selp.b32 s, 0, 0xffffffff, p;\n"
-            " lop3.b32 %0, %0, m, s, 0x60;\n}"
-            : "+r"(peers)
-            : "r"(d), "r"(1u << b));
+        if (BITS <= 9) {
+            // peers &= ballot(bit b set) ^ (bit b set ? 0 : ~0), spelled out so that it stays four instructions
+            // (test, vote, select, lop3); nvcc otherwise shifts, tests twice and selects per bit
+            asm volatile(
+                "{\n .reg .pred p;\n .reg .b32 m, s;\n"
+                " and.b32 s, %1, %2;\n setp.ne.u32 p, s, 0;\n"
+                " vote.sync.ballot.b32 m, p, 0xffffffff;\n"
+                " selp.b32 s, 0, 0xffffffff, p;\n"
+                " lop3.b32 %0, %0, m, s, 0x60;\n}"
+                : "+r"(peers)
+                : "r"(d), "r"(1u << b));
+        } else {
+            // nine or ten bits: ptxas runs out of predicate registers on the spelled-out form
+            const bool     bit = (d & (1u << b)) != 0u;
+            const unsigned m   = __ballot_sync(0xFFFFFFFFu, bit);
+            peers &= m ^ (bit ? 0u : 0xFFFFFFFFu);
+        }
     }
     return peers;
 }
 
-template <typename KeyT, int THREADS, int ITEMS, int RBITS, int MIN_BLOCKS, bool USE_MATCH>
+// HI: the digit lies entirely in the upper 32 bits of a 64-bit key (every pass of the tile sort), so it is a
+// shift and a mask of one register; otherwise a funnel shift over both words.
+template <typename KeyT, int THREADS, int ITEMS, int RBITS, int MIN_BLOCKS, bool USE_MATCH, bool HI>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                          const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
@@ -191,7 +202,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const uint32_t num_tiles = (uint32_t)((n + TILE - 1) / TILE);
     const uint32_t q0        = warp * (ITEMS * 32) + lane;  // warp-striped: item j sits at q0 + 32*j
     const bool     is_digit  = tid < RADIX;
-    const bool     hi_word   = shift >= 32;  // uniform: the digit lives entirely in the key's high word
     uint32_t* const my_hist  = s_wh + warp * RADIX;
     const uint32_t  my_hist_addr = (uint32_t)__cvta_generic_to_shared(my_hist);
     // every key has digit 0 in this pass (the top bits of the depth keys): the pass is the identity
@@ -199,9 +209,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     if ((flags & kSweepSkipIfTrivial) && __ldg(hist) == (uint32_t)n) return;
     const bool ablate_stores = flags & kSweepAblateStores, ablate_lookback = flags & kSweepAblateLookback;  // tuning only
 
-    auto digit_of = [&](KeyT k) -> uint32_t {
-        return hi_word ? key_digit_hi(k, shift, mask) : key_digit(k, shift, mask);
-    };
+    auto digit_of = [&](KeyT k) -> uint32_t { return HI ? key_digit_hi(k, shift, mask) : key_digit(k, shift, mask); };
     auto tile_valid = [&](uint32_t t) -> uint32_t {
         const size_t base = (size_t)t * TILE;
         return (uint32_t)((n - base) < (size_t)TILE ? (n - base) : (size_t)TILE);
@@ -243,9 +251,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             t_prev = t;
         }
     };
-    while (tile < num_tiles) {
-        const uint32_t nvalid = tile_valid(tile);
-        const bool     full   = nvalid == (uint32_t)TILE;
+    // One tile; `full_c` makes "every slot of the tile holds a pair" a compile-time fact (all tiles but the last),
+    // which removes the per-item bounds predicates and the extra ballot for the invalid flag.
+    auto process_tile = [&](auto full_c, const uint32_t nvalid) {
+        constexpr bool full = decltype(full_c)::value;
         if (tid == 0) s_ticket[1] = atomicAdd(ticket, 1u);  // published by the barrier after ranking
 
         // ---- rank inside the warp (s_wh is zero on entry): lanes with the same digit are found with
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         for (int j = 0; j < ITEMS; j++) {
             const bool     valid  = full || q0 + 32 * j < nvalid;
             const uint32_t d      = valid ? digit_of(key[j]) : (uint32_t)RADIX;
-            const unsigned peers  = full ? digit_peers<RBITS, USE_MATCH>(d) : digit_peers<RBITS + 1, USE_MATCH>(d);
+            const unsigned peers  = digit_peers<full ? RBITS : RBITS + 1, USE_MATCH>(d);
             const unsigned lower  = peers & lt_mask;
             uint32_t       before = 0;
             if (valid && lower == 0u) before = atom_shared_add(my_hist_addr + d * 4u, (uint32_t)__popc(peers));
@@ -382,6 +391,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         lap(5);  // write-out
         if (dbg && tid == 0) atomicAdd(dbg + 10, 1ull);
         tile = next_tile;
+    };
+    while (tile < num_tiles) {
+        const uint32_t nvalid = tile_valid(tile);
+        if (nvalid == (uint32_t)TILE) process_tile(std::true_type{}, nvalid);
+        else process_tile(std::false_type{}, nvalid);
         // s_ticket[1] is rewritten at the next loop top, after every thread has read it (three barriers
         // ago); s_keys / s_vals are rewritten after three more barriers, by which time every thread has
         // finished the loop above; s_scan is rewritten before the next barrier, read before the last one
@@ -404,59 +418,34 @@ __global__ void __launch_bounds__(256)
 
 template <typename KeyT>
 struct SweepVariant {
-    void (*kernel)(const KeyT*, KeyT*, const uint32_t*, uint32_t*, size_t, const uint32_t*, size_t, const uint32_t*, uint32_t*,
-                   uint32_t*, int, uint32_t, int, unsigned long long*);
+    using Kernel = void (*)(const KeyT*, KeyT*, const uint32_t*, uint32_t*, size_t, const uint32_t*, size_t, const uint32_t*,
+                            uint32_t*, uint32_t*, int, uint32_t, int, unsigned long long*);
+    Kernel      kernel[2];  // [0] digit anywhere below bit 32 or across it, [1] digit in the upper word (64-bit keys)
     int         threads, tile, radix_bits, blocks_per_sm;
     size_t      smem;
     const char* name;
 };
-#define LCGS_SWEEP(K, T, I, R, B, M) \
-    { onesweep_pass_kernel<K, T, I, R, B, M>, T, T * I, R, B, sweep_smem_bytes<K, T, I, R>(), #T "x" #I " r" #R " " #B "/SM" }
+#define LCGS_SWEEP64(T, I, R, B, M)                                                                                         \
+    { { onesweep_pass_kernel<unsigned long long, T, I, R, B, M, false>, onesweep_pass_kernel<unsigned long long, T, I, R, B, M, true> }, \
+      T, T * I, R, B, sweep_smem_bytes<unsigned long long, T, I, R>(), #T "x" #I " r" #R " " #B "/SM" }
+#define LCGS_SWEEP32(T, I, R, B, M)                                                                    \
+    { { onesweep_pass_kernel<uint32_t, T, I, R, B, M, false>, onesweep_pass_kernel<uint32_t, T, I, R, B, M, false> }, \
+      T, T * I, R, B, sweep_smem_bytes<uint32_t, T, I, R>(), #T "x" #I " r" #R " " #B "/SM" }
 
-// (tile<<32 | depth) instance keys; LCGS_SORT_VARIANT selects another geometry (tuning only)
+// (tile<<32 | depth) instance keys; LCGS_SORT_VARIANT selects another geometry (tuning only).  The geometries
+// that lost the sweeps (profiles/README.md) are no longer compiled.
 static const SweepVariant<unsigned long long> kSweep64[] = {
-    LCGS_SWEEP(unsigned long long, 512, 8, 9, 2, true),  // default: 9-bit digits, 2 CTAs x 16 warps per SM
-    LCGS_SWEEP(unsigned long long, 512, 8, 8, 2, true),
-    LCGS_SWEEP(unsigned long long, 256, 16, 8, 2, true),
-    LCGS_SWEEP(unsigned long long, 256, 16, 8, 3, true),
-    LCGS_SWEEP(unsigned long long, 512, 12, 9, 1, true),
-    LCGS_SWEEP(unsigned long long, 1024, 8, 9, 1, true),
-    LCGS_SWEEP(unsigned long long, 512, 6, 9, 2, true),
-    LCGS_SWEEP(unsigned long long, 256, 8, 8, 4, true),
-    LCGS_SWEEP(unsigned long long, 512, 8, 7, 2, true),   // 8: 7-bit digits (13 tile bits = 7 + 6)
-    LCGS_SWEEP(unsigned long long, 256, 16, 7, 3, true),  // 9
-    LCGS_SWEEP(unsigned long long, 256, 16, 7, 2, true),  // 10
-    LCGS_SWEEP(unsigned long long, 512, 12, 7, 1, true),  // 11
-    LCGS_SWEEP(unsigned long long, 1024, 12, 7, 1, true), // 12: one 12288-pair tile per SM
-    LCGS_SWEEP(unsigned long long, 1024, 16, 7, 1, true), // 13: one 16384-pair tile per SM
-    LCGS_SWEEP(unsigned long long, 1024, 8, 7, 1, true),  // 14
-    LCGS_SWEEP(unsigned long long, 512, 8, 7, 2, false),  // 15: ballot ranking instead of MATCH.ANY
-    LCGS_SWEEP(unsigned long long, 256, 16, 7, 3, false), // 16
-    LCGS_SWEEP(unsigned long long, 512, 8, 9, 2, false),  // 17
-    LCGS_SWEEP(unsigned long long, 256, 16, 7, 4, false), // 18
-    LCGS_SWEEP(unsigned long long, 256, 12, 7, 4, false), // 19
-    LCGS_SWEEP(unsigned long long, 256, 8, 7, 6, false),  // 20
-    LCGS_SWEEP(unsigned long long, 128, 16, 7, 8, false), // 21
-    LCGS_SWEEP(unsigned long long, 256, 20, 7, 2, false), // 22
-    LCGS_SWEEP(unsigned long long, 256, 24, 7, 2, false), // 23
-    LCGS_SWEEP(unsigned long long, 384, 16, 7, 2, false), // 24
-    LCGS_SWEEP(unsigned long long, 256, 28, 7, 2, false), // 25
-    LCGS_SWEEP(unsigned long long, 128, 32, 7, 4, false), // 26
+    LCGS_SWEEP64(512, 8, 9, 2, true),    // 0: 9-bit digits, MATCH.ANY ranking: long keys (reference flow, 45 bits = 5 passes)
+    LCGS_SWEEP64(512, 8, 9, 2, false),   // 1: 9-bit digits, ballot ranking: 15..18 key bits (8K frames)
+    LCGS_SWEEP64(256, 20, 7, 2, false),  // 2: 7-bit digits, ballot ranking, 5120-pair tiles: <= 14 key bits (fused flow)
+    LCGS_SWEEP64(256, 12, 7, 4, false),  // 3: same, 3072-pair tiles, 4 CTAs/SM
+    LCGS_SWEEP64(512, 8, 7, 2, true),    // 4: 7-bit digits, MATCH.ANY ranking (the earlier default)
 };
 // 32-bit depth keys of the per-Gaussian sort
 static const SweepVariant<uint32_t> kSweep32[] = {
-    LCGS_SWEEP(uint32_t, 512, 8, 9, 2, true),
-    LCGS_SWEEP(uint32_t, 512, 8, 8, 2, true),
-    LCGS_SWEEP(uint32_t, 256, 16, 8, 3, true),
-    LCGS_SWEEP(uint32_t, 512, 4, 9, 3, true),
-    LCGS_SWEEP(uint32_t, 256, 8, 8, 4, true),
-    LCGS_SWEEP(uint32_t, 512, 8, 9, 2, false),  // 5: ballot ranking
-    LCGS_SWEEP(uint32_t, 512, 8, 9, 3, false),  // 6
-    LCGS_SWEEP(uint32_t, 512, 4, 9, 4, false),  // 7
-    LCGS_SWEEP(uint32_t, 512, 12, 9, 2, false), // 8
-    LCGS_SWEEP(uint32_t, 512, 16, 9, 1, false), // 9
-    LCGS_SWEEP(uint32_t, 512, 24, 9, 1, false), // 10
-    LCGS_SWEEP(uint32_t, 1024, 8, 9, 1, false), // 11
+    LCGS_SWEEP32(512, 16, 9, 1, false),  // 0: one 8192-pair tile per SM, ballot ranking
+    LCGS_SWEEP32(512, 8, 9, 2, false),   // 1
+    LCGS_SWEEP32(512, 8, 9, 2, true),    // 2: MATCH.ANY ranking (the earlier default)
 };
 constexpr int kMinSweepTile = 2048;
 constexpr size_t kHistSlotBytes = (size_t)kMaxSortPasses * kMaxRadix * sizeof(uint32_t);  // 16 KB, 256-byte multiple
@@ -491,8 +480,8 @@ static int sweep_variant_index(int bits)
     // measured: two 7-bit ballot passes for up to 14 tile bits (256 x 20, 2 CTAs/SM); two 9-bit ballot passes up to
     // 18 bits (the 8K frame's 17 tile bits: 4.8 ms vs 5.4 ms with MATCH); MATCH ranking for longer keys
     // (the reference flow's 45 bits = 5 passes: 1.11 ms vs 1.17 ms with ten ballots per item)
-    if (sizeof(KeyT) == 8) return bits <= 14 ? 22 : (bits <= 18 ? 17 : 0);
-    return 9;                                            // depth keys: 9-bit digits, one 8192-pair tile per SM
+    if (sizeof(KeyT) == 8) return bits <= 14 ? 2 : (bits <= 18 ? 1 : 0);
+    return 0;                                            // depth keys: 9-bit digits, one 8192-pair tile per SM
 }
 
 // workspace layout: [hist slot 0][hist slot 1][status: passes*tiles*RADIX u32][tmp keys][tmp vals], a
@@ -610,7 +599,8 @@ static int launch_sort_t(lcgs_b200_ctx* ctx, const SortPlan<KeyT>& plan, const K
     // opt in to > 48 KB of dynamic shared memory, once per context (function attributes are per device)
     bool& attr_set = ctx->sweep_attr_set[sizeof(KeyT) == 8 ? 1 : 0][plan.variant];
     if (!attr_set) {
-        LCGS_CUDA_CHECK(ctx, cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
+        for (int h = 0; h < 2; h++)
+            LCGS_CUDA_CHECK(ctx, cudaFuncSetAttribute(var.kernel[h], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
         attr_set = true;
     }
     const size_t   max_ctas     = (size_t)ctx->num_sms * var.blocks_per_sm;
@@ -651,7 +641,8 @@ static int launch_sort_t(lcgs_b200_ctx* ctx, const SortPlan<KeyT>& plan, const K
             alt->alt_vals  = src_v;
             alt->last_hist = plan.hist + (size_t)p * radix;
         }
-        var.kernel<<<sweep_blocks, var.threads, var.smem, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
+        const int hi = (sizeof(KeyT) == 8 && info.shift[p] >= 32) ? 1 : 0;
+        var.kernel[hi]<<<sweep_blocks, var.threads, var.smem, s>>>(src_k, dst_k, src_v, dst_v, n_host, d_n, capacity,
                                                               plan.hist + (size_t)p * radix,
                                                               plan.status + (size_t)p * tiles * radix, ticket + p,
                                                               info.shift[p], info.mask[p],
