@@ -271,7 +271,7 @@ LCGS_B200_API int lcgs_b200_peer_free(lcgs_b200_ctx* ctx, void* dev_ptr);  /* fr
 
 /* ---- tuning hook (no reference counterpart) ---- */
 
-/* Makes kernels DROP parts of their work (bit mask, see kAblate* in csrc/common.cuh) so that the cost of
+/* Makes kernels DROP parts of their work (bit mask, see kAblate* / kDebug* in csrc/common.cuh) so that the cost of
  * one part can be measured on a real frame (scripts/ablate.py).  Results are wrong while the mask is
  * non-zero; the default 0 is the only production value.  Process-wide. */
 LCGS_B200_API void lcgs_b200_debug_ablate(int mask);

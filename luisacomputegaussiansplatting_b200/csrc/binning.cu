@@ -339,7 +339,7 @@ int launch_duplicate_keys(lcgs_b200_ctx* ctx, int P, int W, int H, const float* 
     return LCGS_B200_OK;
 }
 
-int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, const SortedPairsU32& sorted,
+int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, int H, const SortedPairsU32& sorted,
                                  const uint2* rects, uint64_t* keys, uint32_t* vals, size_t capacity, int row0,
                                  const SortDigits* digits, cudaStream_t s)
 {
@@ -351,9 +351,11 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
         dg = *digits;
     if (dg.num_passes < 2) dg.shift[1] = 32;  // unused, but keep the kernel's shift amounts in range
     const uint32_t gx = (uint32_t)((W + 15) / 16);
-    // index inside a rect / rect width as a multiply-high: exact while j * w < 2^32; j < w * h and the
-    // packed rects hold 16-bit extents, so it is enough that gx * gx * 65535 stays below 2^32
-    const bool     exact_div = (unsigned long long)gx * gx * 65535ull < 0x100000000ull;
+    // index inside a rect / rect width as a multiply-high: exact while j * w < 2^32; j < w * h with w <= gx and
+    // h <= gy, so it is enough that gx * gx * gy stays below 2^32 (an 8K frame: 480 * 480 * 270 = 6.2e7).
+    // kDebugDupSlowPath forces the general path (division, owner search by shuffle) so that tests can reach it.
+    const uint32_t gy        = (uint32_t)((H + 15) / 16);
+    const bool     exact_div = (unsigned long long)gx * gx * gy < 0x100000000ull && !(g_ablate & kDebugDupSlowPath);
     const uint32_t tiles     = (uint32_t)(((size_t)P + kEmitTile - 1) / kEmitTile);
     int            rc        = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * sizeof(unsigned long long));
     if (rc) return rc;

@@ -136,7 +136,7 @@ static int splat_tail(lcgs_b200_ctx* ctx, int P, const lcgs_b200_frame* fr, cons
         mark(ctx, s);
         if ((rc = sort_prepare_u64(ctx, fr->list_capacity, 32, g.end_bit, &dg64, s))) return rc;
         const bool hist64 = dg64.hist && dg64.num_passes >= 1 && dg64.num_passes <= 2;
-        if ((rc = launch_duplicate_keys_sorted(ctx, d_m, P, g.W, sorted, o.rects, fr->point_list_keys_unsorted, fr->point_list_unsorted, fr->list_capacity,
+        if ((rc = launch_duplicate_keys_sorted(ctx, d_m, P, g.W, g.H, sorted, o.rects, fr->point_list_keys_unsorted, fr->point_list_unsorted, fr->list_capacity,
                                                g.row0, hist64 ? &dg64 : nullptr, s)))
             return rc;
         mark(ctx, s);

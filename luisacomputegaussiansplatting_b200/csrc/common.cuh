@@ -105,6 +105,9 @@ int ws_reserve(lcgs_b200_ctx* ctx, Workspace& ws, size_t bytes);
 extern int g_ablate;
 constexpr int kAblateSortStores = 1, kAblateSortLookback = 2, kAblateDupHist = 4, kAblateDupStores = 8, kAblateDupGather = 16,
               kAblateCompactHist = 32, kAblateCompactDepth = 64;
+// Not an ablation (results stay exact): take the emission kernel's general path -- integer division and owner search
+// by shuffle, otherwise only used for grids beyond gx * gx * gy >= 2^32 -- so that tests can cover it.
+constexpr int kDebugDupSlowPath = 128;
 
 // stage launchers (one group per .cu); all enqueue on `s` and return an lcgs_b200_status
 int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b200_view_params* vp,
@@ -114,7 +117,7 @@ int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const
                         uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, const SortDigits* digits,
                         cudaStream_t s);
 struct SortedPairsU32;
-int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, const SortedPairsU32& sorted,
+int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, int H, const SortedPairsU32& sorted,
                                  const uint2* rects, uint64_t* keys, uint32_t* vals, size_t capacity, int row0,
                                  const SortDigits* digits, cudaStream_t s);
 // digit layout of a prepared sort, for kernels that accumulate its histograms while producing the keys

@@ -378,3 +378,17 @@ def test_far_gaussians_run_the_fourth_depth_pass(lcgs, dev):
     fr = _render_and_compare(lcgs, dev, sc2, pose, 320, 200)
     touching = fr.tiles_touched > 0
     assert (fr.depth[touching] > 13200.0).sum() > 100 and (fr.depth[touching] < 100.0).sum() > 100
+
+
+def test_emission_general_path(lcgs, dev):
+    """The instance emission normally maps a slot of a Gaussian's rect to (x, y) by multiply-high and finds the
+    owning Gaussian with a ballot; grids with gx * gx * gy >= 2^32 take integer division and a shuffle search
+    instead.  The debug hook forces that path on a small frame; results must not change."""
+    from luisacomputegaussiansplatting_b200 import _capi
+    lib = _capi.load()
+    sc, pose = make_case("C3", 5000, 384, 240)
+    lib.lcgs_b200_debug_ablate(128)
+    try:
+        _render_and_compare(lcgs, dev, sc, pose, 384, 240, scale_modifier=6.0)
+    finally:
+        lib.lcgs_b200_debug_ablate(0)
