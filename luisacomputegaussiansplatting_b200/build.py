@@ -8,6 +8,8 @@ the repository snapshot.  Flags that matter:
 """
 from __future__ import annotations
 
+import fcntl
+import hashlib
 import os
 import subprocess
 import sys
@@ -27,13 +29,28 @@ NVCC_FLAGS = [
 ]
 
 
+STAMP = LIB + ".stamp"  # digest of the sources the shipped .so was built from (travels with it to the GPU box)
+
+
 def _mtime(path: str) -> float:
     return os.path.getmtime(path) if os.path.exists(path) else 0.0
 
 
+def _source_digest() -> str:
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    newest = max([_mtime(os.path.join(CSRC, f)) for f in SOURCES + HEADERS] + [_mtime(__file__)])
-    return _mtime(LIB) < newest
+    """Content-based (file times do not survive the copy to another box): the .so is stale iff it is missing
+    or its stamp does not match the digest of the sources + flags."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
+        return True
+    with open(STAMP) as fh:
+        return fh.read().strip() != _source_digest()
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
@@ -42,6 +59,18 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(NVCC):
         raise RuntimeError("nvcc not found at %s and %s is missing or stale" % (NVCC, LIB))
     os.makedirs(BUILD, exist_ok=True)
+    # several ranks of one job may get here together: one builds, the others wait and find a fresh library
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB
+            return _build_native_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_native_locked(verbose: bool) -> str:
     log_path = os.path.join(BUILD, "ptxas.log")
 
     def compile_one(src: str):
@@ -62,11 +91,16 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             sys.stderr.write(r.stderr)
     objs = [o for _, o, _ in results]
-    link = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++"]
+    tmp = "%s.tmp.%d" % (LIB, os.getpid())  # link aside, then rename: nobody ever maps a half-written library
+    link = [NVCC, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    os.replace(tmp, LIB)
+    with open(STAMP + ".tmp", "w") as fh:
+        fh.write(_source_digest() + "\n")
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 
