@@ -23,12 +23,7 @@ constexpr int kRecordFloat4s = 3;
 // depth < 0.2 * 2^16 they fit in 27 bits = three 9-bit digits, and the fourth pass skips itself.
 constexpr uint32_t kDepthKeyBase = 0x3E4CCCCDu;
 
-// Radix sort geometry (onesweep): 8-bit digits.
-constexpr int kRadixBits      = 8;
-constexpr int kRadix          = 1 << kRadixBits;
-constexpr int kSortThreads    = 256;
-constexpr int kSortItems      = 16;
-constexpr int kSortTile       = kSortThreads * kSortItems;  // 4096 pairs per tile
+// Radix sort (onesweep, sort.cu): at most 8 passes (64 key bits in 9-bit digits).
 constexpr int kMaxSortPasses  = 8;
 
 // Scan geometry (decoupled look-back).

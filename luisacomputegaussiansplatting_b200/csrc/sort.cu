@@ -2,13 +2,15 @@
 // pairs.  Replaces lcpp DeviceRadixSort<>::SortPairs<ulong,uint> (call site
 // lcgs/src/gs_tile_splatter/impl.cpp:134-144), which the reference's README calls crude.
 //
-// One histogram kernel reads the keys once and counts every digit of every pass; then one
-// "onesweep" kernel per digit reads each pair once and writes it once to its final place for that
-// pass: tiles are ranked in shared memory with warp-match (__match_any_sync) histograms, the
-// per-digit global offsets come from a decoupled look-back across tiles (a window of predecessors
-// in flight per step), and pairs are staged through shared memory so that global stores are
-// coalesced runs.  The next tile's keys are prefetched into registers behind the current tile's
-// look-back and write-out.  Digits are 9 bits wide (45 key bits = 5 passes instead of 6).
+// One histogram kernel reads the keys once and counts every digit of every pass (in the fused frame the
+// kernels that PRODUCE the keys accumulate the histograms instead); then one "onesweep" kernel per digit
+// reads each pair once and writes it once to its final place for that pass: tiles are ranked in shared
+// memory per warp (lanes with equal digits found with one ballot per digit bit, or MATCH.ANY for long keys;
+// one shared-memory atomic per group), the per-digit global offsets come from a decoupled look-back across
+// tiles (a window of predecessors in flight per step), and keys and values are staged through shared memory
+// so that global stores are coalesced runs.  The next tile's keys are prefetched into registers behind the
+// current tile's look-back and write-out.  Digits are 7 bits wide for the fused frame's tile sort (13 bits =
+// 2 passes) and 9 bits otherwise (27-bit depth keys = 3 passes, 45 key bits = 5 passes).
 // Stable: ties keep their input order, so equal (tile, depth) keys stay ordered by Gaussian index,
 // exactly what the CPU oracle's stable sort yields.
 //
@@ -620,10 +622,8 @@ static int launch_sort_t(lcgs_b200_ctx* ctx, const SortPlan<KeyT>& plan, const K
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
         cudaMemset(dbg, 0, sizeof(h));
         if (h[10])
-            fprintf(stderr, "[sort dbg] tiles %llu cycles/tile: rank %llu prefix %llu scatter %llu lookback(t0) %llu lb-wait %llu write %llu | "
-                            "lookback steps/tile %.2f spins/tile %.2f\n",
-                    h[10], h[0] / h[10], h[1] / h[10], h[2] / h[10], h[3] / h[10], h[4] / h[10], h[5] / h[10],
-                    (double)h[8] / h[10], (double)h[9] / h[10]);
+            fprintf(stderr, "[sort dbg] tiles %llu cycles/tile: rank %llu prefix %llu scatter %llu lookback(t0) %llu lb-wait %llu write %llu\n",
+                    h[10], h[0] / h[10], h[1] / h[10], h[2] / h[10], h[3] / h[10], h[4] / h[10], h[5] / h[10]);
     }
     const int ablate = ((g_ablate & kAblateSortStores) ? kSweepAblateStores : 0) | ((g_ablate & kAblateSortLookback) ? kSweepAblateLookback : 0);
     const KeyT*     src_k = kin;

@@ -1,4 +1,4 @@
-# usage: VARIANTS="8 10 14" bash scripts/tune_tilesort.sh   -- tile sort timing per onesweep geometry (+ phase timers)
+# usage: VARIANTS="2 3 4" bash scripts/tune_tilesort.sh   -- tile sort timing per onesweep geometry (+ phase timers)
 mkdir -p gpurun_out
 for v in ${VARIANTS:-2 3 4}; do
   LCGS_SORT_VARIANT=$v timeout 300 python scripts/tune_tilesort.py 2>&1 | grep -E "variant" | tail -1
