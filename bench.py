@@ -20,8 +20,9 @@ on.  Prints ONE JSON line on rank 0.
              built offline) on the host cores of this box, same scene and camera
 
 N > 1 (torchrun): the Gaussian set is replicated, every rank renders its own frame per step and the
-finished frames are gathered to rank 0 over NCCL inside the timed region (view sharding, weak
-scaling).  --impl reference times the CPU oracle instead (rank 0 only).
+finished frames reach rank 0 inside the timed region (view sharding, weak scaling): by default every
+rank's blend kernel stores straight into rank 0's peer-mapped ring over NVLink (--gather peer, the
+gather is fused into the render); --gather nccl uses an overlapped dist.gather instead.  --impl reference times the CPU oracle instead (rank 0 only).
 """
 from __future__ import annotations
 
