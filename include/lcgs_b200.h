@@ -266,6 +266,8 @@ LCGS_B200_API int lcgs_b200_peer_alloc(lcgs_b200_ctx* ctx, size_t bytes, void** 
 /* Other ranks (other processes, other GPUs of the node): map the owner's buffer; enables peer access. */
 LCGS_B200_API int lcgs_b200_peer_open(lcgs_b200_ctx* ctx, const unsigned char handle[LCGS_B200_PEER_HANDLE_BYTES],
                                       void** dev_ptr);
+/* Owner: synchronous copy of `bytes` from the buffer (dev_ptr may point anywhere inside it) to host memory. */
+LCGS_B200_API int lcgs_b200_peer_read(lcgs_b200_ctx* ctx, const void* dev_ptr, void* host_ptr, size_t bytes);
 LCGS_B200_API int lcgs_b200_peer_close(lcgs_b200_ctx* ctx, void* dev_ptr); /* unmap (other ranks) */
 LCGS_B200_API int lcgs_b200_peer_free(lcgs_b200_ctx* ctx, void* dev_ptr);  /* free (owner) */
 

@@ -94,6 +94,7 @@ _PROTOS = {
     "lcgs_b200_sort_breakdown": (_I, [_VP, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I)]),
     "lcgs_b200_peer_alloc": (_I, [_VP, _SZ, C.POINTER(_VP), C.c_char_p]),
     "lcgs_b200_peer_open": (_I, [_VP, C.c_char_p, C.POINTER(_VP)]),
+    "lcgs_b200_peer_read": (_I, [_VP, _VP, _VP, _SZ]),
     "lcgs_b200_peer_close": (_I, [_VP, _VP]),
     "lcgs_b200_peer_free": (_I, [_VP, _VP]),
     "lcgs_b200_debug_ablate": (None, [_I]),

@@ -594,6 +594,15 @@ int lcgs_b200_peer_open(lcgs_b200_ctx* ctx, const unsigned char handle[LCGS_B200
     return LCGS_B200_OK;
 }
 
+int lcgs_b200_peer_read(lcgs_b200_ctx* ctx, const void* dev_ptr, void* host_ptr, size_t bytes)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, dev_ptr && host_ptr, "peer_read: null pointer");
+    LCGS_CUDA_CHECK(ctx, cudaMemcpy(host_ptr, dev_ptr, bytes, cudaMemcpyDeviceToHost));
+    return LCGS_B200_OK;
+}
+
 int lcgs_b200_peer_close(lcgs_b200_ctx* ctx, void* dev_ptr)
 {
     int rc = enter(ctx);

@@ -370,14 +370,11 @@ class PeerBuffer:
 
     def to_host(self, offset_bytes: int, count: int) -> np.ndarray:
         """float32 view of [offset, offset + 4*count) copied to the host (synchronises the device)."""
-        out = torch.empty(count, dtype=torch.float32).pin_memory()
+        out = np.empty(count, dtype=np.float32)
         torch.cuda.synchronize()
-        from cuda.bindings import runtime as cudart  # host copy from raw device memory
-
-        err, = cudart.cudaMemcpy(out.data_ptr(), self.ptr + offset_bytes, 4 * count, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
-        if int(err) != 0:
-            raise RuntimeError("cudaMemcpy from peer buffer failed: %s" % err)
-        return out.numpy().copy()
+        d = self.device
+        d.check(d.lib.lcgs_b200_peer_read(d.ctx, C.c_void_p(self.ptr + offset_bytes), out.ctypes.data_as(C.c_void_p), 4 * count))
+        return out
 
     def close(self):
         if self.ptr:
