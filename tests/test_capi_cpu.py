@@ -53,3 +53,26 @@ def test_no_cpu_fallback():
     assert _capi.load().lcgs_b200_ctx_create(0, C.byref(ctx)) == _capi.ERR_NO_DEVICE
     assert not ctx.value
     assert b"no CPU fallback" in _capi.load().lcgs_b200_status_string(_capi.ERR_NO_DEVICE)
+
+
+def test_library_staleness_is_content_based():
+    """The shipped .so is matched to the sources by a digest stamp, not by file times (which do not survive the copy
+    to the GPU box: ranks of one job once raced to rebuild the library in place)."""
+    from luisacomputegaussiansplatting_b200 import build as b
+
+    assert os.path.exists(b.LIB) and os.path.exists(b.STAMP)
+    assert not b.is_stale()
+    src = os.path.join(b.CSRC, b.SOURCES[0])
+    st = os.stat(src)
+    try:
+        os.utime(src, (st.st_atime, st.st_mtime + 10_000))  # a newer file time alone must not trigger a rebuild
+        assert not b.is_stale()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+    stamp = open(b.STAMP).read()
+    try:
+        open(b.STAMP, "w").write("0" * 64 + "\n")              # a different digest must
+        assert b.is_stale()
+    finally:
+        open(b.STAMP, "w").write(stamp)
+    assert not b.is_stale()
