@@ -37,13 +37,61 @@ def _frame(sc, pose, row0=0, row1=-1):
     return orc.forward(sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, vp, row0=row0, row1=row1)
 
 
+class MemmapRing:
+    """Stand-in for distributed.PeerFrameRing on CPU: the "peer-mapped device buffer" is a file every rank maps;
+    ptr(slot) is a byte offset into it.  Same interface, same barriers."""
+
+    def __init__(self, path, slots, dst=0):
+        self.slots, self.dst, self.group = slots, dst, None
+        self.frame_bytes = 3 * H * W * 4
+        if dist.get_rank() == dst:
+            np.zeros(slots * 3 * H * W, np.float32).tofile(path)
+        dist.barrier()
+        self.mem = np.memmap(path, dtype=np.float32, mode="r+", shape=(slots, 3, H, W))
+
+    def ptr(self, slot):
+        assert 0 <= slot < self.slots
+        return slot * self.frame_bytes
+
+    def write(self, ptr, img, rows=None):
+        slot = ptr // self.frame_bytes
+        if rows is None:
+            self.mem[slot] = img
+        else:
+            self.mem[slot][:, rows[0]:rows[1], :] = img[:, rows[0]:rows[1], :]
+
+    def complete(self):
+        self.mem.flush()
+        dist.barrier()
+
+    def frame(self, slot):
+        return np.array(self.mem[slot])
+
+    def release(self):
+        dist.barrier()
+
+
 def _worker(rank, world, port, mode, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sc = _scene()
     try:
-        if mode == "views":
+        if mode in ("views_peer", "rows_peer"):
+            ring = MemmapRing("/tmp/lcgs_ring_%d.bin" % port, slots=5)
+            if mode == "views_peer":
+                out = D.render_sweep_view_sharded_peer(
+                    lambda k, ptr: ring.write(ptr, _frame(sc, scenes.orbit_pose(k * 13)).img), 5, ring)
+                if rank == 0:
+                    q.put(out)
+            else:
+                pose = (scenes.CAM_POS, scenes.CAM_TARGET, scenes.WORLD_UP_COLMAP)
+                img, bands = D.render_frame_tile_row_sharded_peer(
+                    lambda r0, r1, ptr: ring.write(ptr, _frame(sc, pose, r0, r1).img, (min(H, 16 * r0), min(H, 16 * r1))),
+                    H, ring, slot=2)
+                if rank == 0:
+                    q.put((img, bands))
+        elif mode == "views":
             nviews = 5  # odd on purpose: the last round has an idle rank
             out = D.render_sweep_view_sharded(lambda k: torch.from_numpy(_frame(sc, scenes.orbit_pose(k * 13)).img.copy()),
                                               nviews)
@@ -88,6 +136,21 @@ def test_tile_row_sharded_frame_equals_single_device_frame(mode):
     img, bands = _run(mode)
     want = _frame(_scene(), (scenes.CAM_POS, scenes.CAM_TARGET, scenes.WORLD_UP_COLMAP)).img
     assert bands[0][0] == 0 and bands[-1][1] == (H + 15) // 16 and bands[0][1] == bands[1][0]
+    assert np.array_equal(img.view(np.uint32), want.view(np.uint32))
+
+
+def test_peer_drivers_assemble_the_same_frames():
+    """The drivers of the gather-fused-into-the-render path (every rank writes straight into the destination's
+    buffer; on a GPU box that buffer is peer-mapped device memory, here a shared file)."""
+    frames = _run("views_peer")
+    sc = _scene()
+    assert len(frames) == 5
+    for k, f in enumerate(frames):
+        want = _frame(sc, scenes.orbit_pose(k * 13)).img
+        assert np.array_equal(f.view(np.uint32), want.view(np.uint32)), k
+    img, bands = _run("rows_peer")
+    want = _frame(sc, (scenes.CAM_POS, scenes.CAM_TARGET, scenes.WORLD_UP_COLMAP)).img
+    assert bands[0][0] == 0 and bands[-1][1] == (H + 15) // 16
     assert np.array_equal(img.view(np.uint32), want.view(np.uint32))
 
 
