@@ -15,7 +15,11 @@
  *
  * Threading: a context belongs to one host thread / one GPU at a time (the reference's modules
  * are not thread-safe either: mutable lazily-filled members, buffer_filler.h:56).  Use one context
- * per GPU.
+ * per GPU, and ONE in-flight stream per context: the device scalars (num_rendered, tickets), the
+ * look-back status words and the sort / record / order workspaces are per-context singletons, so
+ * frames enqueued on two streams of one context would corrupt each other.  Frames enqueued back
+ * to back on the same stream pipeline safely (every frame carries its own capacity check on the
+ * device, see lcgs_b200_num_rendered).
  */
 #ifndef LCGS_B200_H
 #define LCGS_B200_H
@@ -33,7 +37,7 @@ extern "C" {
 #define LCGS_B200_API __attribute__((visibility("default")))
 #endif
 
-#define LCGS_B200_VERSION 100 /* 0.1.0 */
+#define LCGS_B200_VERSION 200 /* 0.2.0 */
 
 typedef enum lcgs_b200_status {
     LCGS_B200_OK              = 0,
@@ -85,6 +89,10 @@ typedef struct lcgs_b200_scene {
     const float* sh;
     const float* opacity;
     float        scale_modifier; /* GSProjectorInputProxy::scale_modifier, gs_projector.h:21 */
+    /* extension, optional (NULL = computed per frame): per-Gaussian constants of the alpha test,
+     * [P][2] float32 = (power threshold, log2(opacity)), a pure function of `opacity` written once per
+     * scene by lcgs_b200_scene_prepare.  8-byte aligned.  Must be refreshed whenever opacity changes. */
+    const float* alpha_consts;
 } lcgs_b200_scene;
 
 /* Caller-owned buffers of one frame: the union of GSTileSplatterInputProxy, GSTileSplatterAccelProxy
@@ -100,7 +108,7 @@ typedef struct lcgs_b200_frame {
     float* conic;    /* [P][3] optional; cov2d after project, conic after allocate_tiles (in-place) */
     float* color;    /* [P][3] optional */
     /* GSTileSplatterAccelProxy */
-    uint32_t* tiles_touched;            /* [P] */
+    uint32_t* tiles_touched;            /* [P]; 16-byte aligned buffers take the vector path, others a scalar one */
     uint32_t* point_offsets;            /* [P] inclusive sum */
     uint64_t* point_list_keys_unsorted; /* [L] */
     uint32_t* point_list_unsorted;      /* [L] */
@@ -114,6 +122,10 @@ typedef struct lcgs_b200_frame {
     /* extension: render only tile rows [tile_row_begin, tile_row_end) (multi-GPU tile-row split);
      * tile_row_end < 0 means all rows.  Tile ids in keys/ranges are relative to tile_row_begin. */
     int tile_row_begin, tile_row_end;
+    /* extension, optional (NULL = off): the blend kernel ALSO writes the image the app saves
+     * (app/main.cpp:322-337): interleaved HWC uint8 [H][W][3], vertically flipped (row i = image row
+     * H-1-i), uint8(v * 255) with truncation.  4x fewer bytes to read back than target_img. */
+    uint8_t* target_rgb8;
 } lcgs_b200_frame;
 
 /* ---- library / context ------------------------------------------------------------------- */
@@ -229,7 +241,9 @@ LCGS_B200_API int lcgs_b200_render(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc
 
 /* The value GSTileSplatter::forward returns (impl.cpp:179): synchronises `stream` (the one the
  * last whole-frame call was enqueued on) and stores that frame's num_rendered.  Returns LCGS_B200_ERR_CAPACITY if it exceeded
- * list_capacity (the frame's image is then incomplete). */
+ * list_capacity (the frame's image is then incomplete).  The comparison is made ON THE DEVICE by the
+ * frame itself (an overflow flag travels back with the count), so it is right for pipelined frames with
+ * different capacities and for CUDA-graph replays. */
 LCGS_B200_API int lcgs_b200_num_rendered(lcgs_b200_ctx* ctx, lcgs_b200_stream stream, int* num_rendered);
 
 /* Pipelined variant of the above: enqueue a copy of the last enqueued frame's num_rendered into
@@ -240,6 +254,20 @@ LCGS_B200_API int lcgs_b200_read_num_rendered_async(lcgs_b200_ctx* ctx, uint32_t
  * memory on `stream`. */
 LCGS_B200_API int lcgs_b200_read_image(lcgs_b200_ctx* ctx, const lcgs_b200_frame* frame, float* host_img,
                                        lcgs_b200_stream stream);
+
+/* The same read-back for the fused uint8 image (frame->target_rgb8, 3*W*H bytes). */
+LCGS_B200_API int lcgs_b200_read_image_rgb8(lcgs_b200_ctx* ctx, const lcgs_b200_frame* frame, uint8_t* host_rgb,
+                                            lcgs_b200_stream stream);
+
+/* Per-scene constants of the alpha test (see lcgs_b200_scene::alpha_consts): consts[P][2] =
+ * (smallest power that passes alpha >= 1/255 for this opacity, log2(opacity)).  Enqueue only. */
+LCGS_B200_API int lcgs_b200_scene_prepare(lcgs_b200_ctx* ctx, int num_gaussians, const float* opacity, float* consts,
+                                          lcgs_b200_stream stream);
+
+/* Display::_transpose_shader, app/display.cpp:30-39: planar CHW float image -> [H][W] RGBA8 (the BYTE4
+ * framebuffer the viewer presents): unorm8 = round-to-nearest(clamp(v, 0, 1) * 255), alpha = 255, no flip. */
+LCGS_B200_API int lcgs_b200_transpose_rgba8(lcgs_b200_ctx* ctx, int width, int height, const float* img_chw,
+                                            uint8_t* rgba, lcgs_b200_stream stream);
 
 /* ---- per-stage timing (the reference has a single wall clock, app/main.cpp:225-226,317) ---- */
 
@@ -268,15 +296,29 @@ LCGS_B200_API int lcgs_b200_peer_open(lcgs_b200_ctx* ctx, const unsigned char ha
                                       void** dev_ptr);
 /* Owner: synchronous copy of `bytes` from the buffer (dev_ptr may point anywhere inside it) to host memory. */
 LCGS_B200_API int lcgs_b200_peer_read(lcgs_b200_ctx* ctx, const void* dev_ptr, void* host_ptr, size_t bytes);
+/* Owner: the same copy enqueued on `stream` (host_ptr should be pinned); no synchronisation. */
+LCGS_B200_API int lcgs_b200_peer_read_async(lcgs_b200_ctx* ctx, const void* dev_ptr, void* host_ptr, size_t bytes,
+                                            lcgs_b200_stream stream);
 LCGS_B200_API int lcgs_b200_peer_close(lcgs_b200_ctx* ctx, void* dev_ptr); /* unmap (other ranks) */
 LCGS_B200_API int lcgs_b200_peer_free(lcgs_b200_ctx* ctx, void* dev_ptr);  /* free (owner) */
 
-/* ---- tuning hook (no reference counterpart) ---- */
-
-/* Makes kernels DROP parts of their work (bit mask, see kAblate* / kDebug* in csrc/common.cuh) so that the cost of
- * one part can be measured on a real frame (scripts/ablate.py).  Results are wrong while the mask is
- * non-zero; the default 0 is the only production value.  Process-wide. */
-LCGS_B200_API void lcgs_b200_debug_ablate(int mask);
+/* Device-side flow control for such a buffer: 32-bit sequence words that live in it (owner's memory) let a
+ * writer tell the owner "slot s holds frame j" and the owner tell the writer "slot s may be overwritten",
+ * entirely in stream order -- no host synchronisation and no collective between frames.
+ *   signal: after everything enqueued before it on `stream` has completed (the frame's stores included), store
+ *           `value` to *flag with system-scope release semantics (works through a peer mapping).
+ *   wait:   hold `stream` until *flag >= value (system-scope acquire; one polling thread).  Gives up after
+ *           timeout_ms (then sets the context's sticky flow-control error, see lcgs_b200_peer_error) so that a
+ *           dead peer can never hang the GPU. */
+LCGS_B200_API int lcgs_b200_peer_signal(lcgs_b200_ctx* ctx, uint32_t* flag, uint32_t value, lcgs_b200_stream stream);
+LCGS_B200_API int lcgs_b200_peer_wait(lcgs_b200_ctx* ctx, const uint32_t* flag, uint32_t value, uint32_t timeout_ms,
+                                      lcgs_b200_stream stream);
+/* Synchronises the device; *timed_out = number of waits that gave up since the context was created. */
+LCGS_B200_API int lcgs_b200_peer_error(lcgs_b200_ctx* ctx, uint32_t* timed_out);
+/* The consumer's read of a delivered frame: *out (device memory, 8-byte aligned) = wrap-around sum of the `num_words`
+ * 32-bit words at `data` (16-byte aligned), as one 64-bit integer -- exact and independent of the summation order. */
+LCGS_B200_API int lcgs_b200_checksum_u32(lcgs_b200_ctx* ctx, const void* data, size_t num_words, uint64_t* out,
+                                         lcgs_b200_stream stream);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,8 @@ class ViewParams(C.Structure):
 
 class Scene(C.Structure):
     _fields_ = [("num_gaussians", C.c_int), ("sh_deg", C.c_int), ("pos", C.c_void_p), ("scale", C.c_void_p),
-                ("rotq", C.c_void_p), ("sh", C.c_void_p), ("opacity", C.c_void_p), ("scale_modifier", C.c_float)]
+                ("rotq", C.c_void_p), ("sh", C.c_void_p), ("opacity", C.c_void_p), ("scale_modifier", C.c_float),
+                ("alpha_consts", C.c_void_p)]
 
 
 class Frame(C.Structure):
@@ -50,7 +51,8 @@ class Frame(C.Structure):
                 ("point_offsets", C.c_void_p), ("point_list_keys_unsorted", C.c_void_p),
                 ("point_list_unsorted", C.c_void_p), ("point_list_keys", C.c_void_p), ("point_list", C.c_void_p),
                 ("ranges", C.c_void_p), ("list_capacity", C.c_size_t), ("target_img", C.c_void_p),
-                ("radii", C.c_void_p), ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int)]
+                ("radii", C.c_void_p), ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int),
+                ("target_rgb8", C.c_void_p)]
 
 
 PEER_HANDLE_BYTES = 64
@@ -89,15 +91,22 @@ _PROTOS = {
     "lcgs_b200_num_rendered": (_I, [_VP, _VP, C.POINTER(_I)]),
     "lcgs_b200_read_num_rendered_async": (_I, [_VP, _VP, _VP]),
     "lcgs_b200_read_image": (_I, [_VP, C.POINTER(Frame), _VP, _VP]),
+    "lcgs_b200_read_image_rgb8": (_I, [_VP, C.POINTER(Frame), _VP, _VP]),
+    "lcgs_b200_scene_prepare": (_I, [_VP, _I, _VP, _VP, _VP]),
+    "lcgs_b200_transpose_rgba8": (_I, [_VP, _I, _I, _VP, _VP, _VP]),
     "lcgs_b200_set_profiling": (_I, [_VP, _I]),
     "lcgs_b200_stage_times": (_I, [_VP, C.POINTER(_F)]),
     "lcgs_b200_sort_breakdown": (_I, [_VP, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I)]),
     "lcgs_b200_peer_alloc": (_I, [_VP, _SZ, C.POINTER(_VP), C.c_char_p]),
     "lcgs_b200_peer_open": (_I, [_VP, C.c_char_p, C.POINTER(_VP)]),
     "lcgs_b200_peer_read": (_I, [_VP, _VP, _VP, _SZ]),
+    "lcgs_b200_peer_read_async": (_I, [_VP, _VP, _VP, _SZ, _VP]),
     "lcgs_b200_peer_close": (_I, [_VP, _VP]),
     "lcgs_b200_peer_free": (_I, [_VP, _VP]),
-    "lcgs_b200_debug_ablate": (None, [_I]),
+    "lcgs_b200_peer_signal": (_I, [_VP, _VP, C.c_uint32, _VP]),
+    "lcgs_b200_peer_wait": (_I, [_VP, _VP, C.c_uint32, C.c_uint32, _VP]),
+    "lcgs_b200_peer_error": (_I, [_VP, C.POINTER(C.c_uint32)]),
+    "lcgs_b200_checksum_u32": (_I, [_VP, _VP, _SZ, _VP, _VP]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 
@@ -113,6 +122,17 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    if os.environ.get("LCGS_TUNING") == "1":  # scripts/tune_*.py only: the -DLCGS_TUNING library, built explicitly
+        path = _build.TUNING_LIB
+        if not os.path.exists(path):
+            raise RuntimeError("LCGS_TUNING=1 but %s is missing: run `python -m luisacomputegaussiansplatting_b200.build --tuning`" % path)
+        lib = C.CDLL(path)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
     path = _build.LIB
     if not os.path.exists(path) or _build.is_stale():
         try:

@@ -30,6 +30,9 @@ NVCC_FLAGS = [
 
 
 STAMP = LIB + ".stamp"  # digest of the sources the shipped .so was built from (travels with it to the GPU box)
+# -DLCGS_TUNING build (kernel geometries selectable by environment variable, extra sweep variants): a SEPARATE library
+# that only scripts/tune_*.py load (LCGS_TUNING=1); the production library has none of it.
+TUNING_LIB = os.path.join(HERE, "liblcgs_b200_tuning.so")
 
 
 def _mtime(path: str) -> float:
@@ -70,12 +73,20 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             fcntl.flock(lock, fcntl.LOCK_UN)
 
 
-def _build_native_locked(verbose: bool) -> str:
-    log_path = os.path.join(BUILD, "ptxas.log")
+def build_tuning(verbose: bool = False) -> str:
+    """Always rebuilds liblcgs_b200_tuning.so (-DLCGS_TUNING)."""
+    os.makedirs(BUILD, exist_ok=True)
+    return _build_native_locked(verbose, tuning=True)
+
+
+def _build_native_locked(verbose: bool, tuning: bool = False) -> str:
+    log_path = os.path.join(BUILD, "ptxas_tuning.log" if tuning else "ptxas.log")
+    out_lib = TUNING_LIB if tuning else LIB
+    extra = ["-DLCGS_TUNING"] if tuning else []
 
     def compile_one(src: str):
-        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-        cmd = [NVCC, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(BUILD, src.replace(".cu", ".tuning.o" if tuning else ".o"))
+        cmd = [NVCC, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
 
@@ -91,13 +102,15 @@ def _build_native_locked(verbose: bool) -> str:
         if verbose:
             sys.stderr.write(r.stderr)
     objs = [o for _, o, _ in results]
-    tmp = "%s.tmp.%d" % (LIB, os.getpid())  # link aside, then rename: nobody ever maps a half-written library
+    tmp = "%s.tmp.%d" % (out_lib, os.getpid())  # link aside, then rename: nobody ever maps a half-written library
     link = [NVCC, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    os.replace(tmp, LIB)
+    os.replace(tmp, out_lib)
+    if tuning:
+        return out_lib
     with open(STAMP + ".tmp", "w") as fh:
         fh.write(_source_digest() + "\n")
     os.replace(STAMP + ".tmp", STAMP)
@@ -136,6 +149,32 @@ def build_app(force: bool = False) -> str:
     return APP_BIN
 
 
+FACADE_TEST_SRC = os.path.join(HERE, "..", "tests", "facade", "test_facade.cpp")
+FACADE_TEST_BIN = os.path.join(HERE, "..", "tests", "facade", "test_facade")
+
+
+def build_facade_test(force: bool = False) -> str:
+    """tests/facade/test_facade: the reference's GSTileSplatter::forward call sequence and a 16-byte-float3 camera
+    compiled against the C++ facade (checks that the facade keeps the reference's argument lists)."""
+    lib = build_native()
+    newest = max([_mtime(f) for f in _app_deps()] + [_mtime(lib), _mtime(FACADE_TEST_SRC)])
+    if not force and _mtime(FACADE_TEST_BIN) >= newest:
+        return FACADE_TEST_BIN
+    cmd = ["g++", "-O1", "-std=c++20", "-Wall", "-Wextra", "-Wno-missing-field-initializers"]
+    for inc in APP_INCLUDES:
+        cmd += ["-I", inc]
+    cmd += [FACADE_TEST_SRC, os.path.join(APP_DIR, "gaussians.cpp"), "-o", FACADE_TEST_BIN, "-L", HERE, "-llcgs_b200",
+            "-Wl,-rpath," + HERE, "-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("building tests/facade/test_facade failed")
+    return FACADE_TEST_BIN
+
+
 if __name__ == "__main__":
+    if "--tuning" in sys.argv:
+        print(build_tuning(verbose=True))
+        sys.exit(0)
     print(build_native(force="--force" in sys.argv, verbose=True))
     print(build_app(force="--force" in sys.argv))

@@ -5,15 +5,59 @@
 //   opacity         -> sigmoid,  scale_k -> exp,  rot_k -> normalised quaternion (r,x,y,z)
 #include "gaussians.h"
 
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <sstream>
+#include <thread>
+#include <unordered_set>
 
 namespace lcgs
 {
+
+namespace
+{
+std::mutex                g_pinned_mutex;
+std::unordered_set<void*> g_pinned;  // blocks that came from cudaHostAlloc (the rest came from malloc)
+}  // namespace
+
+void* host_alloc_pinned(size_t bytes)
+{
+    if (bytes == 0) bytes = 1;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess && p) {
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        g_pinned.insert(p);
+        return p;
+    }
+    (void)cudaGetLastError();  // no device / out of pinned memory: pageable memory still works, just slower
+    p = std::malloc(bytes);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+
+void host_free_pinned(void* p)
+{
+    if (!p) return;
+    bool pinned;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        pinned = g_pinned.erase(p) != 0;
+    }
+    if (pinned) cudaFreeHost(p);
+    else std::free(p);
+}
 
 float GaussiansData::opacity_activation(float x) { return 1.0f / (1.0f + std::exp(-x)); }
 float GaussiansData::scaling_activation(float x) { return std::exp(x); }
@@ -60,7 +104,7 @@ bool fail(std::string* err, const std::string& msg)
 }
 }  // namespace
 
-bool read_gs_ply(GaussiansData& gs, const std::filesystem::path& fpath, std::string* err)
+bool read_gs_ply(GaussiansData& gs, const std::filesystem::path& fpath, std::string* err, int threads)
 {
     std::ifstream in(fpath, std::ios::binary);
     if (!in) return fail(err, "cannot open " + fpath.string());
@@ -146,20 +190,48 @@ bool read_gs_ply(GaussiansData& gs, const std::filesystem::path& fpath, std::str
     gs.resize((int)count);
     float* arrays[5] = { gs.pos.data(), gs.feature.data(), gs.opacity.data(), gs.scale.data(), gs.rotq.data() };
 
-    if (binary) {
-        const size_t      chunk_rows = 65536;
-        std::vector<char> buf((size_t)stride * chunk_rows);
-        for (long base = 0; base < count; base += (long)chunk_rows) {
-            const size_t rows = (size_t)std::min<long>((long)chunk_rows, count - base);
-            in.read(buf.data(), (std::streamsize)(rows * stride));
-            if ((size_t)in.gcount() != rows * (size_t)stride) return fail(err, "truncated PLY body");
-            for (size_t k = 0; k < props.size(); k++) {
-                if (dst[k].arr == NONE) continue;
-                float*      out = arrays[dst[k].arr] + (size_t)base * dst[k].stride + dst[k].off;
-                const char* src = buf.data() + props[k].offset;
-                for (size_t r = 0; r < rows; r++) std::memcpy(out + r * dst[k].stride, src + r * stride, 4);
-            }
+    auto activate = [&](long g0, long g1) {
+        for (long g = g0; g < g1; g++) {
+            gs.opacity[g] = GaussiansData::opacity_activation(gs.opacity[g]);
+            for (int c = 0; c < 3; c++) gs.scale[3 * g + c] = GaussiansData::scaling_activation(gs.scale[3 * g + c]);
+            GaussiansData::rotation_activation(gs.rotq[4 * g], gs.rotq[4 * g + 1], gs.rotq[4 * g + 2], gs.rotq[4 * g + 3]);
         }
+    };
+    if (binary) {
+        // map the body; every worker de-interleaves and activates its own range of rows
+        const std::streamoff body = in.tellg();
+        in.close();
+        const size_t need_bytes = (size_t)count * (size_t)stride;
+        const int    fd         = ::open(fpath.c_str(), O_RDONLY);
+        if (fd < 0) return fail(err, "cannot open " + fpath.string());
+        struct stat st;
+        if (fstat(fd, &st) != 0 || (size_t)st.st_size < (size_t)body + need_bytes) {
+            ::close(fd);
+            return fail(err, "truncated PLY body");
+        }
+        const size_t map_len = (size_t)body + need_bytes;
+        void*        map     = map_len ? mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+        ::close(fd);
+        if (map_len && map == MAP_FAILED) return fail(err, "mmap failed");
+        if (map_len) madvise(map, map_len, MADV_SEQUENTIAL);
+        const char* base = static_cast<const char*>(map) + body;
+        int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+        nt     = std::max(1, std::min(nt, (int)((count + 65535) / 65536)));
+        auto work = [&](long g0, long g1) {
+            for (long g = g0; g < g1; g++) {
+                const char* row = base + (size_t)g * stride;
+                for (size_t k = 0; k < props.size(); k++)
+                    if (dst[k].arr != NONE)
+                        std::memcpy(arrays[dst[k].arr] + (size_t)g * dst[k].stride + dst[k].off, row + props[k].offset, 4);
+            }
+            activate(g0, g1);
+        };
+        std::vector<std::thread> pool;
+        const long               per = (count + nt - 1) / nt;
+        for (int t = 1; t < nt; t++) pool.emplace_back(work, std::min<long>(count, t * per), std::min<long>(count, (t + 1) * per));
+        work(0, std::min<long>(count, per));
+        for (auto& th : pool) th.join();
+        if (map_len) munmap(map, map_len);
     } else {
         for (long g = 0; g < count; g++)
             for (size_t k = 0; k < props.size(); k++) {
@@ -167,11 +239,7 @@ bool read_gs_ply(GaussiansData& gs, const std::filesystem::path& fpath, std::str
                 if (!(in >> v)) return fail(err, "truncated ascii PLY body");
                 if (dst[k].arr != NONE) arrays[dst[k].arr][(size_t)g * dst[k].stride + dst[k].off] = (float)v;
             }
-    }
-    for (long g = 0; g < count; g++) {
-        gs.opacity[g] = GaussiansData::opacity_activation(gs.opacity[g]);
-        for (int c = 0; c < 3; c++) gs.scale[3 * g + c] = GaussiansData::scaling_activation(gs.scale[3 * g + c]);
-        GaussiansData::rotation_activation(gs.rotq[4 * g], gs.rotq[4 * g + 1], gs.rotq[4 * g + 2], gs.rotq[4 * g + 3]);
+        activate(0, count);
     }
     return true;
 }

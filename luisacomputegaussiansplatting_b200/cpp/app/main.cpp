@@ -5,7 +5,8 @@
 //   --backend <name> (accepted; always CUDA here, but it still names the output file)
 //   --out <dir> (default "out")         --world colmap|blender      --exp_N <frames>      --help / -h
 // Output: <out>/<plyname>_<backend>.png, CHW -> HWC with vertical flip and truncating *255
-// (main.cpp:322-339).  The camera pose is the reference's hard-coded one (main.cpp:191-202).
+// (main.cpp:322-339) -- in the fused path that conversion is the blend kernel's epilogue, so 3 bytes per
+// pixel cross PCIe instead of 12.  The camera pose is the reference's hard-coded one (main.cpp:191-202).
 // Extensions: --dump <dir> writes the frame's raw buffers, --fused 0 drives the three reference
 // entry points separately instead of the fused frame call, --capacity sets the instance list size L.
 // --display (ImGui viewer) is out of scope and rejected.
@@ -223,8 +224,16 @@ int main(int argc, char** argv)
                                           d_keys,          d_list,          d_ranges };
     lcgs::GSTileSplatterInputProxy  input{ P, bg_color, d_means_2d, d_depth_features, d_covs_2d, d_color, d_opacity };
 
+    // fused path: per-scene alpha-test constants (a function of the opacities only) and the uint8 output image
+    auto d_alpha_consts = device.create_buffer<float>(fused ? (size_t)P * 2 : 1);
+    auto d_rgb8         = device.create_buffer<uint8_t>(fused ? (size_t)w * h * 3 : 1);
     lcgs_b200_scene scene{ P, 3, d_pos.view().ptr, d_scale.view().ptr, d_rotq.view().ptr, d_sh.view().ptr,
-                           d_opacity.view().ptr, 1.0f };
+                           d_opacity.view().ptr, 1.0f, nullptr };
+    if (fused) {
+        device.check(lcgs_b200_scene_prepare(device.ctx(), P, d_opacity.view().ptr, d_alpha_consts.view().ptr, stream.abi()),
+                     "lcgs_b200_scene_prepare");
+        scene.alpha_consts = d_alpha_consts.view().ptr;
+    }
     lcgs_b200_frame frame{};
     frame.width = w; frame.height = h;
     frame.means_2d = d_means_2d.view().ptr; frame.depth = d_depth_features.view().ptr; frame.conic = d_covs_2d.view().ptr;
@@ -235,8 +244,9 @@ int main(int argc, char** argv)
     frame.ranges = d_ranges.view().ptr; frame.list_capacity = L;
     frame.target_img = d_img.view().ptr; frame.radii = d_radii.view().ptr;
     frame.tile_row_begin = 0; frame.tile_row_end = -1;
+    frame.target_rgb8 = fused ? d_rgb8.view().ptr : nullptr;
 
-    lcgs::CommandList cmd_list(stream);
+    lcgs::CommandList cmd_list;
     int               num_rendered = 0;
     for (int exp_i = 0; exp_i < exp_N; ++exp_i) {
         if (fused) {
@@ -246,6 +256,7 @@ int main(int argc, char** argv)
         } else {
             sh_processor.process(cmd_list, { P, 3, d_pos }, cam, d_sh, d_color, 3, 3);
             projector.forward(cmd_list, { P, d_pos, d_scale, d_rotq, 1.0f }, { d_means_2d, d_covs_2d, d_depth_features }, cam);
+            stream << cmd_list.commit();  // main.cpp:270
             num_rendered = tile_splatter.forward(device, stream, accel, input, output);
         }
     }
@@ -255,9 +266,11 @@ int main(int argc, char** argv)
         device.check(rc, "lcgs_b200_num_rendered");
     }
 
-    std::vector<float> h_img((size_t)w * h * 3);
-    std::vector<int>   h_radii((size_t)P);
-    stream.download(d_img.view(), h_img.data());
+    std::vector<float>   h_img(fused ? 0 : (size_t)w * h * 3);
+    std::vector<uint8_t> rgb((size_t)w * h * 3);
+    std::vector<int>     h_radii((size_t)P);
+    if (fused) stream.download(d_rgb8.view(), rgb.data());  // already HWC / flipped / uint8
+    else stream.download(d_img.view(), h_img.data());
     stream.download(d_radii.view(), h_radii.data());
     stream.synchronize();
     const double exp_time = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
@@ -266,14 +279,14 @@ int main(int argc, char** argv)
     std::printf("fps: %f with test N %d\n", 1000.0 / (exp_time / (exp_N > 0 ? exp_N : 1)), exp_N);
 
     // 3 x H x W -> H x W x 3, vertical flip, truncating *255 (main.cpp:322-337)
-    std::vector<uint8_t> rgb((size_t)w * h * 3);
-    const size_t         plane = (size_t)w * h;
-    for (int i = 0; i < h; i++)
-        for (int j = 0; j < w; j++) {
-            const size_t px  = ((size_t)i * w + j) * 3;
-            const size_t idx = (size_t)(h - i - 1) * w + j;
-            for (int c = 0; c < 3; c++) rgb[px + c] = (uint8_t)(h_img[c * plane + idx] * 255);
-        }
+    const size_t plane = (size_t)w * h;
+    if (!fused)
+        for (int i = 0; i < h; i++)
+            for (int j = 0; j < w; j++) {
+                const size_t px  = ((size_t)i * w + j) * 3;
+                const size_t idx = (size_t)(h - i - 1) * w + j;
+                for (int c = 0; c < 3; c++) rgb[px + c] = (uint8_t)(h_img[c * plane + idx] * 255);
+            }
     const std::string img_name = out_dir + "/" + ply_name + "_" + backend + ".png";
     if (!lcgs::write_png_rgb8(img_name, w, h, rgb.data())) lcgs::fatal("cannot write " + img_name);
     std::printf("result saved in %s\n", img_name.c_str());

@@ -33,10 +33,12 @@ public:
         if (!use_focal) fatal("GSProjector::forward(use_focal=false) is unreachable from the app and not implemented");
         lcgs_b200_view_params vp;
         lcgs_b200_view_params_from_camera(abi(cam), &vp);
-        m_device->check(lcgs_b200_project(m_device->ctx(), input.num_gaussians, input.pos.ptr, input.scale.ptr,
-                                          input.rotq.ptr, input.scale_modifier, &vp, output.means_2d.ptr, output.depth.ptr,
-                                          output.covs_2d.ptr, cmdlist.stream().abi()),
-                        "GSProjector::forward");
+        cmdlist << [dev = m_device, input, output, vp](cudaStream_t s) {
+            dev->check(lcgs_b200_project(dev->ctx(), input.num_gaussians, input.pos.ptr, input.scale.ptr, input.rotq.ptr,
+                                         input.scale_modifier, &vp, output.means_2d.ptr, output.depth.ptr, output.covs_2d.ptr,
+                                         reinterpret_cast<lcgs_b200_stream>(s)),
+                       "GSProjector::forward");
+        };
     }
 };
 

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -45,6 +46,11 @@ inline void cuda_check(cudaError_t e, const char* what)
     if (e != cudaSuccess) fatal(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+// A unit of work that is enqueued on the stream its command list is committed to: the stand-in for
+// luisa::compute::Command.  As in LuisaCompute, `cmdlist << command` only RECORDS the command;
+// `stream << cmdlist.commit()` enqueues the recorded commands in order and `<< synchronize()` waits.
+using Command = std::function<void(cudaStream_t)>;
+
 template <typename T>
 struct BufferView {
     T*     ptr   = nullptr;
@@ -53,6 +59,19 @@ struct BufferView {
     T*           data() const noexcept { return ptr; }
     BufferView   subview(size_t offset, size_t n) const noexcept { return { ptr + offset, n }; }
     explicit     operator bool() const noexcept { return ptr != nullptr; }
+    // `cmdlist << view.copy_to(host)` / `<< view.copy_from(host)` (app/main.cpp:216-222,313-315, impl.cpp:106)
+    Command copy_to(void* host) const
+    {
+        return [p = ptr, n = count, host](cudaStream_t s) {
+            cuda_check(cudaMemcpyAsync(host, p, n * sizeof(T), cudaMemcpyDeviceToHost, s), "copy_to");
+        };
+    }
+    Command copy_from(const void* host) const
+    {
+        return [p = ptr, n = count, host](cudaStream_t s) {
+            cuda_check(cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, s), "copy_from");
+        };
+    }
 };
 
 class Stream;
@@ -85,6 +104,8 @@ public:
     BufferView<T> view(size_t offset, size_t n) const noexcept { return { m_ptr + offset, n }; }
     BufferView<T> subview(size_t offset, size_t n) const noexcept { return view(offset, n); }
     operator BufferView<T>() const noexcept { return view(); }
+    Command       copy_to(void* host) const { return view().copy_to(host); }
+    Command       copy_from(const void* host) const { return view().copy_from(host); }
 
 private:
     void release() noexcept
@@ -96,6 +117,12 @@ private:
     size_t m_n   = 0;
 };
 
+struct CommitToken {         // what CommandList::commit() hands to `stream << ...`: the recorded commands
+    std::vector<Command> commands;
+};
+struct SynchronizeToken {};  // luisa::compute::synchronize()
+inline SynchronizeToken synchronize() noexcept { return {}; }
+
 class Stream
 {
 public:
@@ -106,6 +133,14 @@ public:
     cudaStream_t     handle() const noexcept { return m_s; }
     lcgs_b200_stream abi() const noexcept { return reinterpret_cast<lcgs_b200_stream>(m_s); }
     void             synchronize() const { cuda_check(cudaStreamSynchronize(m_s), "cudaStreamSynchronize"); }
+    // `stream << cmdlist.commit() << synchronize()` (impl.cpp:100,107,131,144,146)
+    Stream& operator<<(CommitToken&& t)
+    {
+        for (auto& c : t.commands) c(m_s);
+        return *this;
+    }
+    Stream& operator<<(SynchronizeToken) { synchronize(); return *this; }
+    Stream& operator<<(const Command& c) { c(m_s); return *this; }
     template <typename T>
     void upload(BufferView<T> dst, const T* host) const
     {
@@ -121,17 +156,27 @@ private:
     cudaStream_t m_s = nullptr;
 };
 
-// A CommandList is bound to a stream; appended work is enqueued immediately, commit() is a no-op
-// kept for source compatibility with `stream << cmdlist.commit()`.
+// luisa::compute::CommandList: records commands until commit() (impl.cpp:87-177 appends kernels, fills, the
+// scan, the sort and a read-back to one list and commits it five times).
 class CommandList
 {
 public:
-    explicit CommandList(Stream& s) : m_stream(&s) {}
-    Stream& stream() const noexcept { return *m_stream; }
-    CommandList& commit() noexcept { return *this; }
+    CommandList() = default;
+    CommandList& operator<<(Command c)
+    {
+        m_commands.push_back(std::move(c));
+        return *this;
+    }
+    CommitToken commit() noexcept
+    {
+        CommitToken t{ std::move(m_commands) };
+        m_commands.clear();
+        return t;
+    }
+    bool empty() const noexcept { return m_commands.empty(); }
 
 private:
-    Stream* m_stream;
+    std::vector<Command> m_commands;
 };
 
 class Device

@@ -24,9 +24,11 @@ public:
                  int channel = 3, int level = 3) noexcept
     {
         (void)level;
-        m_device->check(lcgs_b200_sh_process(m_device->ctx(), proxy.N, channel, &camera.position.x, proxy.pos.ptr, sh.ptr,
-                                             color.ptr, cmdlist.stream().abi()),
-                        "SHProcessor::process");
+        cmdlist << [dev = m_device, proxy, cam_pos = camera.position, sh, color, channel](cudaStream_t s) {
+            dev->check(lcgs_b200_sh_process(dev->ctx(), proxy.N, channel, &cam_pos.x, proxy.pos.ptr, sh.ptr, color.ptr,
+                                            reinterpret_cast<lcgs_b200_stream>(s)),
+                       "SHProcessor::process");
+        };
     }
 
 private:

@@ -25,6 +25,23 @@ using float4x4 = std::array<float, 16>;  // column-major, m[c*4+r]
 
 inline const lcgs_b200_camera* abi(const Camera& c) { return reinterpret_cast<const lcgs_b200_camera*>(&c); }
 
+// Field-by-field conversion of ANY camera with the reference's member names into the ABI struct.  The
+// reference's own lcgs::Camera holds four luisa::float3, which are 16-byte aligned 16-byte vectors
+// (lcgs/include/lcgs/util/camera.h:15-25): it is 80 bytes, NOT layout-compatible with the packed 64-byte
+// lcgs_b200_camera, so it must never be reinterpret_cast -- copy the fields (tests/facade/test_facade.cpp
+// checks this against a mock 16-byte float3).
+template <typename CameraLike>
+inline lcgs_b200_camera to_abi_camera(const CameraLike& c) noexcept
+{
+    lcgs_b200_camera o;
+    o.position[0] = c.position.x; o.position[1] = c.position.y; o.position[2] = c.position.z;
+    o.front[0] = c.front.x; o.front[1] = c.front.y; o.front[2] = c.front.z;
+    o.up[0] = c.up.x; o.up[1] = c.up.y; o.up[2] = c.up.z;
+    o.right[0] = c.right.x; o.right[1] = c.right.y; o.right[2] = c.right.z;
+    o.fov = c.fov; o.aspect_ratio = c.aspect_ratio; o.width = c.width; o.height = c.height;
+    return o;
+}
+
 inline Camera get_lookat_cam(float3 pos, float3 target, float3 world_up)
 {
     Camera cam;

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kEmitThreads)
                                  const __grid_constant__ SortedPairsU32 sorted, const uint2* __restrict__ rects,
                                  unsigned long long* status, uint32_t* ticket, unsigned long long* __restrict__ keys,
                                  uint32_t* __restrict__ vals, size_t capacity, const __grid_constant__ SortDigits digits,
-                                 bool exact_div, int ablate)
+                                 bool exact_div)
 {
     // digit histograms of the tile bits of the emitted keys (two passes at most: the tile sort then skips
     // its histogram kernel).  Consecutive lanes emit consecutive tiles of one Gaussian, so the upper digit
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kEmitThreads)
     __shared__ uint32_t s_wsum[kEmitWarps];
     __shared__ uint32_t s_base;
     __shared__ uint32_t s_tk;
-    const bool     do_hist = digits.hist != nullptr && !(ablate & kAblateDupHist);
+    const bool     do_hist = digits.hist != nullptr;
     const int      nbins   = do_hist ? (digits.num_passes << digits.radix_bits) : 0;
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kEmitThreads)
 #pragma unroll
         for (int c = 0; c < kEmitItems; c++) {
             uint2 r = make_uint2(0u, 0u);
-            if (idx[c] != 0xFFFFFFFFu) r = __ldg(rects + ((ablate & kAblateDupGather) ? k0 + 32 * c : idx[c]));
+            if (idx[c] != 0xFFFFFFFFu) r = __ldg(rects + idx[c]);
             xy0[c] = r.x;
             w[c]   = r.y & 0xFFFFu;
             cnt[c] = w[c] * (r.y >> 16);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kEmitThreads)
                 const uint32_t tile = ((o_xy0 & 0xFFFFu) + rx) + ((o_xy0 >> 16) + ry - row0) * gx;
                 const size_t   dst  = (size_t)excl0 + p;
                 const bool     emit = p < total && dst < capacity;
-                if (emit && !(ablate & kAblateDupStores)) {
+                if (emit) {
                     keys[dst] = ((unsigned long long)tile << 32) | (unsigned long long)o_dbits;
                     vals[dst] = o_idx;
                 }
@@ -339,9 +339,9 @@ int launch_duplicate_keys(lcgs_b200_ctx* ctx, int P, int W, int H, const float* 
     return LCGS_B200_OK;
 }
 
-int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, int H, const SortedPairsU32& sorted,
-                                 const uint2* rects, uint64_t* keys, uint32_t* vals, size_t capacity, int row0,
-                                 const SortDigits* digits, cudaStream_t s)
+int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, int H, int num_rows,
+                                 const SortedPairsU32& sorted, const uint2* rects, uint64_t* keys, uint32_t* vals,
+                                 size_t capacity, int row0, const SortDigits* digits, cudaStream_t s)
 {
     if (P <= 0) return LCGS_B200_OK;
     // fused histograms need the digits to live in the tile id (key bits >= 32) and at most two passes
@@ -353,9 +353,10 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
     const uint32_t gx = (uint32_t)((W + 15) / 16);
     // index inside a rect / rect width as a multiply-high: exact while j * w < 2^32; j < w * h with w <= gx and
     // h <= gy, so it is enough that gx * gx * gy stays below 2^32 (an 8K frame: 480 * 480 * 270 = 6.2e7).
-    // kDebugDupSlowPath forces the general path (division, owner search by shuffle) so that tests can reach it.
-    const uint32_t gy        = (uint32_t)((H + 15) / 16);
-    const bool     exact_div = (unsigned long long)gx * gx * gy < 0x100000000ull && !(g_ablate & kDebugDupSlowPath);
+    // Rect heights are bounded by the band's row count, so a band of a huge frame keeps the fast path; the general
+    // path (division, owner search by shuffle) is covered by the extreme-aspect test (640000 x 48 pixels).
+    const uint32_t gy        = (uint32_t)(num_rows > 0 ? num_rows : (H + 15) / 16);
+    const bool     exact_div = (unsigned long long)gx * gx * gy < 0x100000000ull;
     const uint32_t tiles     = (uint32_t)(((size_t)P + kEmitTile - 1) / kEmitTile);
     int            rc        = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * sizeof(unsigned long long));
     if (rc) return rc;
@@ -368,7 +369,7 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
     duplicate_keys_sorted_kernel<<<blocks, kEmitThreads, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, sorted, rects,
                                                                 (unsigned long long*)ctx->scan_ws.ptr, ticket,
                                                                 reinterpret_cast<unsigned long long*>(keys), vals, capacity,
-                                                                dg, exact_div, g_ablate);
+                                                                dg, exact_div);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }
@@ -386,6 +387,77 @@ int launch_ranges(lcgs_b200_ctx* ctx, const uint64_t* keys, size_t n_host, const
     if (blocks > max_blocks) blocks = max_blocks;
     tile_ranges_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(keys), n_host, d_n,
                                                        capacity, ranges, (uint32_t)num_tiles);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+// ---- multi-GPU flow control and the consumer's checksum (include/lcgs_b200.h, peer section) ----------------
+__global__ void peer_signal_kernel(uint32_t* flag, uint32_t value)
+{
+    // kernels of one stream run in order, so every store of the frame has been performed when this kernel starts;
+    // the fence orders them (at system scope: the flag may sit in another GPU's memory) before the flag's store
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+__global__ void peer_wait_kernel(const uint32_t* flag, uint32_t value, long long timeout_cycles, uint32_t* d_timeouts)
+{
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - value) >= 0) break;  // sequence numbers: wrap-around safe
+        if (clock64() - t0 > timeout_cycles) {
+            atomicAdd(d_timeouts, 1u);
+            break;
+        }
+        __nanosleep(500);
+    }
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) checksum_u32_kernel(const uint4* __restrict__ data, size_t num_vec, const uint32_t* __restrict__ tail,
+                                                           uint32_t num_tail, unsigned long long* out)
+{
+    unsigned long long acc = 0;
+    const size_t       stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < num_vec; k += stride) {
+        const uint4 v = __ldcs(data + k);  // streamed: read once
+        acc += (unsigned long long)v.x + v.y + v.z + v.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < num_tail) acc += tail[threadIdx.x];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+int launch_peer_signal(lcgs_b200_ctx* ctx, uint32_t* flag, uint32_t value, cudaStream_t s)
+{
+    peer_signal_kernel<<<1, 1, 0, s>>>(flag, value);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+int launch_peer_wait(lcgs_b200_ctx* ctx, const uint32_t* flag, uint32_t value, uint32_t timeout_ms, cudaStream_t s)
+{
+    // clock64 ticks at the SM clock (<= ~2 GHz): 2e6 cycles per millisecond bounds the wait from above
+    peer_wait_kernel<<<1, 1, 0, s>>>(flag, value, (long long)timeout_ms * 2000000ll, ctx->d_scalars + LCGS_SCALAR_PEER_TIMEOUTS);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+int launch_checksum_u32(lcgs_b200_ctx* ctx, const void* data, size_t num_words, uint64_t* out, cudaStream_t s)
+{
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(out, 0, sizeof(uint64_t), s));
+    if (num_words == 0) return LCGS_B200_OK;
+    const size_t num_vec = num_words / 4;
+    size_t       blocks  = (num_vec + 255) / 256;
+    const size_t max_blocks = (size_t)ctx->num_sms * 4;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks == 0) blocks = 1;
+    checksum_u32_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(data), num_vec,
+                                                         reinterpret_cast<const uint32_t*>(data) + num_vec * 4, (uint32_t)(num_words & 3),
+                                                         reinterpret_cast<unsigned long long*>(out));
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }

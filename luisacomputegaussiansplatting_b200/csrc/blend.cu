@@ -25,8 +25,6 @@
 //
 // Compute-bound (FP32 issue + shared memory), not HBM-bound; HBM side is 4 B id + 48 B record per
 // instance (mostly L2 hits) + 12 B per pixel.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace lcgs_b200 {
@@ -60,15 +58,82 @@ __device__ __forceinline__ float ex2_ftz(float x)
     return y;
 }
 
+// ---- tile schedule: longest list first -----------------------------------------------------------
+// Tile populations are heavy-tailed (a tile in front of the object holds ten times the average list), and
+// the hardware hands CTAs out in blockIdx order: with tiles in row-major order the kernel's tail is
+// whichever long tile happened to start last.  One small CTA buckets the tiles by list length
+// (floating-point-like buckets: exponent + 3 mantissa bits, 12 % granularity) and writes the tile ids in
+// descending bucket order; blend CTA b then renders tile order[b].  The order inside a bucket is
+// whatever the atomics produce -- it changes the schedule only, never a result.
+constexpr int kOrderThreads = 1024;
+constexpr int kOrderBuckets = 256;
+
+__device__ __forceinline__ uint32_t length_bucket(uint32_t len)
+{
+    if (len < 8u) return len;  // 0..7 exact
+    const int e = 31 - __clz(len);  // >= 3
+    return (uint32_t)((e - 2) * 8) + ((len >> (e - 3)) & 7u);  // 8.. : (e-3)*8 + 8 + mantissa
+}
+
+__global__ void __launch_bounds__(kOrderThreads)
+    tile_order_kernel(const uint2* __restrict__ ranges, uint32_t num_tiles, uint32_t* __restrict__ order,
+                      const uint32_t* __restrict__ d_num_rendered, uint32_t capacity, uint32_t* __restrict__ d_flags)
+{
+    // the frame's capacity check, made where the count lives: [0] = overflow flag, [1] = the capacity it was
+    // tested against; both travel back to the host with the count (lcgs_b200_num_rendered)
+    if (d_flags && threadIdx.x == 0) {
+        d_flags[0] = *d_num_rendered > capacity ? 1u : 0u;
+        d_flags[1] = capacity;
+    }
+    __shared__ uint32_t s_cnt[kOrderBuckets], s_base[kOrderBuckets];
+    const int tid = threadIdx.x;
+    if (tid < kOrderBuckets) s_cnt[tid] = 0u;
+    __syncthreads();
+    for (uint32_t t = tid; t < num_tiles; t += kOrderThreads) {
+        const uint2 r = __ldg(ranges + t);
+        atomicAdd(&s_cnt[length_bucket(r.y > r.x ? r.y - r.x : 0u)], 1u);
+    }
+    __syncthreads();
+    // descending exclusive scan over the 256 buckets by one warp (8 buckets per lane)
+    if (tid < 32) {
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            c[k] = s_cnt[kOrderBuckets - 1 - (tid * 8 + k)];
+            sum += c[k];
+        }
+        uint32_t x = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (tid >= d) x += y;
+        }
+        uint32_t run = x - sum;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            s_base[kOrderBuckets - 1 - (tid * 8 + k)] = run;
+            run += c[k];
+        }
+    }
+    __syncthreads();
+    for (uint32_t t = tid; t < num_tiles; t += kOrderThreads) {
+        const uint2 r = __ldg(ranges + t);
+        order[atomicAdd(&s_base[length_bucket(r.y > r.x ? r.y - r.x : 0u)], 1u)] = t;
+    }
+}
+
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
     blend_kernel(int W, int H, uint32_t gx, uint32_t row0, float bg0, float bg1, float bg2,
-                 const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                 const float4* __restrict__ records, const uint32_t* __restrict__ d_num_rendered,
-                 float* __restrict__ img)
+                 const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
+                 const uint32_t* __restrict__ point_list, const float4* __restrict__ records,
+                 const uint32_t* __restrict__ d_num_rendered /* non-null: apply quirk Q10 */, float* __restrict__ img,
+                 uint8_t* __restrict__ rgb8)
 {
     // num_rendered == 0: the reference returns before launching the render and leaves the image
-    // untouched (lcgs/src/gs_tile_splatter/impl.cpp:109, quirk Q10)
+    // untouched (lcgs/src/gs_tile_splatter/impl.cpp:109, quirk Q10).  Only a whole frame does that: the
+    // launcher passes no count for a band of tile rows, whose own instance count says nothing about the
+    // frame's, so a band always writes bg * T to its tiles.
     if (d_num_rendered && *d_num_rendered == 0u) return;
 
     // [buffer][plane][slot]: plane 0 = (pix.x, pix.y, -0.5*conic.x, -conic.y),
@@ -83,7 +148,9 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
     constexpr uint32_t kPlane = kBlendThreads * 16u, kBuf = 3u * kPlane;
 
     // 8x4 pixel patch per warp: warps tile the 16x16 block as 2 columns x 4 rows of patches
-    const int tile_x0 = blockIdx.x * 16, tile_y0 = (row0 + blockIdx.y) * 16;
+    const uint32_t tile    = __ldg(order + blockIdx.x);  // band-local tile id, longest lists first
+    const uint32_t tile_by = tile / gx, tile_bx = tile - tile_by * gx;
+    const int tile_x0 = (int)tile_bx * 16, tile_y0 = (int)(row0 + tile_by) * 16;
     const int patch_x0 = tile_x0 + (warp & 1) * 8, patch_y0 = tile_y0 + (warp >> 1) * 4;
     const int px = patch_x0 + (lane & 7);
     const int py = patch_y0 + (lane >> 3);
@@ -91,7 +158,6 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
     const float pxf = (float)px, pyf = (float)py;  // no half-pixel offset (Q2)
     const float tx0 = (float)tile_x0, ty0 = (float)tile_y0, tx1 = (float)(tile_x0 + 15), ty1 = (float)(tile_y0 + 15);
 
-    const uint32_t tile  = blockIdx.x + blockIdx.y * gx;
     const uint2    range = __ldg(ranges + tile);
     const uint32_t len   = range.y > range.x ? range.y - range.x : 0u;
     const uint32_t nrounds = (len + kBlendThreads - 1) / kBlendThreads;
@@ -204,28 +270,74 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
         T                    = fabsf(T);
         img[pix]             = __fmaf_rn(bg0, T, C0);
         img[pix + plane]     = __fmaf_rn(bg1, T, C1);
-        img[pix + 2 * plane] = __fmaf_rn(bg2, T, C2);
+        const float v0 = __fmaf_rn(bg0, T, C0), v1 = __fmaf_rn(bg1, T, C1), v2 = __fmaf_rn(bg2, T, C2);
+        img[pix]             = v0;
+        img[pix + plane]     = v1;
+        img[pix + 2 * plane] = v2;
+        if (rgb8) {
+            // the app's post-process fused into the epilogue (app/main.cpp:322-337): HWC, vertical flip,
+            // uint8(v * 255) with truncation (cvt.rzi saturates at 0; 255 caps what C leaves undefined)
+            uint8_t* o = rgb8 + ((size_t)(H - 1 - py) * (size_t)W + (size_t)px) * 3;
+            o[0] = (uint8_t)min(__float2uint_rz(v0 * 255.0f), 255u);
+            o[1] = (uint8_t)min(__float2uint_rz(v1 * 255.0f), 255u);
+            o[2] = (uint8_t)min(__float2uint_rz(v2 * 255.0f), 255u);
+        }
     }
 }
 
+// Display::_transpose_shader (app/display.cpp:30-39): planar CHW float -> RGBA8 unorm framebuffer, no flip.
+__global__ void __launch_bounds__(256) transpose_rgba8_kernel(int n, const float* __restrict__ img, uchar4* __restrict__ rgba)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    auto unorm = [](float v) { return (unsigned char)__float2uint_rn(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f); };
+    rgba[p] = make_uchar4(unorm(__ldg(img + p)), unorm(__ldg(img + n + p)), unorm(__ldg(img + 2 * (size_t)n + p)), 255);
+}
+
+int launch_tile_order(lcgs_b200_ctx* ctx, const uint32_t* ranges, int num_tiles, const uint32_t* d_num_rendered,
+                      size_t list_capacity, cudaStream_t s)
+{
+    if (num_tiles <= 0) return LCGS_B200_OK;
+    int rc = ws_reserve(ctx, ctx->tile_order_ws, (size_t)num_tiles * sizeof(uint32_t));
+    if (rc) return rc;
+    const uint32_t cap = (uint32_t)(list_capacity > 0xFFFFFFFFull ? 0xFFFFFFFFull : list_capacity);
+    tile_order_kernel<<<1, kOrderThreads, 0, s>>>(reinterpret_cast<const uint2*>(ranges), (uint32_t)num_tiles,
+                                                  (uint32_t*)ctx->tile_order_ws.ptr, d_num_rendered, cap,
+                                                  d_num_rendered ? ctx->d_scalars + LCGS_SCALAR_OVERFLOW : nullptr);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+// `ranges` must have been ordered by launch_tile_order on the same stream.
 int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32_t* ranges, const uint32_t* point_list,
-                 const float4* records, const uint32_t* d_num_rendered, float* img, int row0, int row1, cudaStream_t s)
+                 const float4* records, const uint32_t* d_num_rendered, float* img, uint8_t* rgb8, int row0, int row1,
+                 cudaStream_t s)
 {
     const uint32_t gx = (uint32_t)((W + 15) / 16), gy = (uint32_t)((H + 15) / 16);
     if (row1 < 0) row1 = (int)gy;
     if (W <= 0 || H <= 0 || row1 <= row0) return LCGS_B200_OK;
-    dim3 grid(gx, (unsigned)(row1 - row0));
-    static int occ = -1;  // LCGS_BLEND_OCC: register budget as "CTAs per SM" (tuning only)
-    if (occ < 0) {
-        const char* e = getenv("LCGS_BLEND_OCC");
-        occ           = e ? atoi(e) : 5;
-    }
+    const uint32_t num_tiles = gx * (uint32_t)(row1 - row0);
+    // Q10 applies to a whole frame only (see the kernel)
+    const bool whole = row0 == 0 && row1 == (int)gy;
+    // 48 registers -> 5 CTAs per SM (measured best of 4 / 5 / 6 / 8)
     auto kern = blend_kernel<5>;
+#ifdef LCGS_TUNING
+    const int occ = LCGS_TUNE_INT("LCGS_BLEND_OCC", 5);
     if (occ == 4) kern = blend_kernel<4>;
     if (occ == 6) kern = blend_kernel<6>;
-    if (occ == 8) kern = blend_kernel<8>;
-    kern<<<grid, kBlendThreads, 0, s>>>(W, H, gx, (uint32_t)row0, bg[0], bg[1], bg[2], reinterpret_cast<const uint2*>(ranges),
-                                        point_list, records, d_num_rendered, img);
+#endif
+    kern<<<num_tiles, kBlendThreads, 0, s>>>(W, H, gx, (uint32_t)row0, bg[0], bg[1], bg[2], reinterpret_cast<const uint2*>(ranges),
+                                             (const uint32_t*)ctx->tile_order_ws.ptr, point_list, records,
+                                             whole ? d_num_rendered : nullptr, img, rgb8);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+int launch_transpose_rgba8(lcgs_b200_ctx* ctx, int W, int H, const float* img, uint8_t* rgba, cudaStream_t s)
+{
+    const long n = (long)W * H;
+    if (n <= 0) return LCGS_B200_OK;
+    transpose_rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int)n, img, reinterpret_cast<uchar4*>(rgba));
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }

@@ -74,6 +74,8 @@ static int frame_geom(lcgs_b200_ctx* ctx, const lcgs_b200_frame* fr, FrameGeom* 
     g->row0 = fr->tile_row_begin;
     g->row1 = fr->tile_row_end < 0 ? (int)g->gy : fr->tile_row_end;
     LCGS_REQUIRE(ctx, g->row0 >= 0 && g->row1 <= (int)g->gy && g->row0 <= g->row1, "frame: bad tile row band");
+    // the fused path packs tile rects into 16-bit fields (preprocess.cu) and tile ids into 32 bits
+    LCGS_REQUIRE(ctx, g->gx < 65536u && g->gy < 65536u, "frame: more than 65535 tiles per row / column");
     g->num_tiles = (int)g->gx * (g->row1 - g->row0);
     // keys are (tile << 32) | depth bits: bits above 32 + ceil(log2(tiles)) are zero, so restricting
     // the sorted bit range is result-identical to the reference's 64-bit sort
@@ -136,8 +138,8 @@ static int splat_tail(lcgs_b200_ctx* ctx, int P, const lcgs_b200_frame* fr, cons
         mark(ctx, s);
         if ((rc = sort_prepare_u64(ctx, fr->list_capacity, 32, g.end_bit, &dg64, s))) return rc;
         const bool hist64 = dg64.hist && dg64.num_passes >= 1 && dg64.num_passes <= 2;
-        if ((rc = launch_duplicate_keys_sorted(ctx, d_m, P, g.W, g.H, sorted, o.rects, fr->point_list_keys_unsorted, fr->point_list_unsorted, fr->list_capacity,
-                                               g.row0, hist64 ? &dg64 : nullptr, s)))
+        if ((rc = launch_duplicate_keys_sorted(ctx, d_m, P, g.W, g.H, g.row1 - g.row0, sorted, o.rects, fr->point_list_keys_unsorted,
+                                               fr->point_list_unsorted, fr->list_capacity, g.row0, hist64 ? &dg64 : nullptr, s)))
             return rc;
         mark(ctx, s);
         if ((rc = sort_run_u64(ctx, fr->point_list_keys_unsorted, fr->point_list_keys, fr->point_list_unsorted,
@@ -160,17 +162,26 @@ static int splat_tail(lcgs_b200_ctx* ctx, int P, const lcgs_b200_frame* fr, cons
     }
     if ((rc = launch_ranges(ctx, fr->point_list_keys, 0, d_n, fr->list_capacity, fr->ranges, g.num_tiles, s))) return rc;
     mark(ctx, s);
+    // tile schedule (longest list first) + the frame's capacity check, made on the device against the count
+    if ((rc = launch_tile_order(ctx, fr->ranges, g.num_tiles, d_n, fr->list_capacity, s))) return rc;
     if ((rc = launch_blend(ctx, g.W, g.H, fr->bg_color, fr->ranges, fr->point_list, (const float4*)ctx->record_ws.ptr, d_n,
-                           fr->target_img, g.row0, g.row1, s)))
+                           fr->target_img, fr->target_rgb8, g.row0, g.row1, s)))
         return rc;
     mark(ctx, s);
-    ctx->h_scalars[2] = (uint32_t)(fr->list_capacity > 0xFFFFFFFFull ? 0xFFFFFFFFull : fr->list_capacity);
-    LCGS_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    // count, overflow flag and the capacity it was tested against travel back together (in stream order, so
+    // pipelined frames with different capacities and graph replays report their own)
+    LCGS_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, LCGS_NUM_SCALARS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     ctx->ev_valid = ctx->profiling ? ctx->ev_count : 0;
     return LCGS_B200_OK;
 }
 
-int g_ablate = 0;
+#ifdef LCGS_TUNING
+int tuning_env_int(const char* name, int fallback)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : fallback;
+}
+#endif
 
 static int reserve_all(lcgs_b200_ctx* ctx, int P, size_t max_instances)
 {
@@ -193,8 +204,6 @@ static int reserve_all(lcgs_b200_ctx* ctx, int P, size_t max_instances)
 extern "C" {
 
 int lcgs_b200_version(void) { return LCGS_B200_VERSION; }
-
-void lcgs_b200_debug_ablate(int mask) { lcgs_b200::g_ablate = mask; }
 
 const char* lcgs_b200_status_string(int status)
 {
@@ -249,6 +258,7 @@ int lcgs_b200_ctx_destroy(lcgs_b200_ctx* ctx)
     if (ctx->sort_ws.ptr) cudaFree(ctx->sort_ws.ptr);
     if (ctx->record_ws.ptr) cudaFree(ctx->record_ws.ptr);
     if (ctx->order_ws.ptr) cudaFree(ctx->order_ws.ptr);
+    if (ctx->tile_order_ws.ptr) cudaFree(ctx->tile_order_ws.ptr);
     sort_free_plans(ctx);
     for (int i = 0; i < 16; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -471,8 +481,10 @@ int lcgs_b200_blend(lcgs_b200_ctx* ctx, int P, int width, int height, const floa
     cudaStream_t s = as_stream(stream);
     if ((rc = launch_build_records(ctx, P, means_2d, conic, opacity, color, tiles_touched, (float4*)ctx->record_ws.ptr, s)))
         return rc;
+    const int gx = (width + 15) / 16, gy = (height + 15) / 16;
+    if ((rc = launch_tile_order(ctx, ranges, gx * ((row1 < 0 ? gy : row1) - row0), nullptr, 0, s))) return rc;
     return launch_blend(ctx, width, height, bg_color, ranges, point_list, (const float4*)ctx->record_ws.ptr, nullptr,
-                        target_img, row0, row1, s);
+                        target_img, nullptr, row0, row1, s);
 }
 
 // ---- whole frame ----------------------------------------------------------------------------------------
@@ -515,16 +527,16 @@ int lcgs_b200_render(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b
     LCGS_REQUIRE(ctx, P >= 0 && sc->sh_deg >= 0 && sc->sh_deg <= 3, "render: bad scene");
     LCGS_REQUIRE(ctx, P == 0 || (sc->pos && sc->scale && sc->rotq && sc->sh && sc->opacity), "render: null scene array");
     LCGS_REQUIRE(ctx, aligned(sc->rotq, 16) && aligned(sc->sh, 16), "render: rotq and sh must be 16-byte aligned");
+    LCGS_REQUIRE(ctx, aligned(sc->alpha_consts, 8), "render: alpha_consts must be 8-byte aligned");
     LCGS_REQUIRE(ctx, aligned(fr->means_2d, 8), "render: means_2d must be 8-byte aligned");
     LCGS_REQUIRE(ctx, vp->width == fr->width && vp->height == fr->height, "render: view/frame resolution mismatch");
     if ((rc = reserve_all(ctx, P > 0 ? P : 1, fr->list_capacity))) return rc;
     cudaStream_t s = as_stream(stream);
     ctx->ev_count  = 0;
     mark(ctx, s);
-    static const bool reference_flow = getenv("LCGS_REFERENCE_FLOW") != nullptr;  // debugging: emit in index order
     if ((rc = launch_preprocess_fused(ctx, sc, vp, fr, (float4*)ctx->record_ws.ptr, order_ws_views(ctx, P).rects, s))) return rc;
     mark(ctx, s);
-    return splat_tail(ctx, P, fr, g, fr->means_2d, !reference_flow, s);
+    return splat_tail(ctx, P, fr, g, fr->means_2d, true, s);
 }
 
 int lcgs_b200_num_rendered(lcgs_b200_ctx* ctx, lcgs_b200_stream stream, int* num_rendered)
@@ -535,8 +547,9 @@ int lcgs_b200_num_rendered(lcgs_b200_ctx* ctx, lcgs_b200_stream stream, int* num
     LCGS_CUDA_CHECK(ctx, cudaStreamSynchronize(as_stream(stream)));
     const uint32_t n = ctx->h_scalars[LCGS_SCALAR_NUM_RENDERED];
     *num_rendered    = (int)n;  // the reference stores the uint count in an int (gs_tile_splatter.h:23)
-    if (n > ctx->h_scalars[2]) {
-        snprintf(ctx->last_error, sizeof(ctx->last_error), "num_rendered %u exceeds list_capacity %u", n, ctx->h_scalars[2]);
+    if (ctx->h_scalars[LCGS_SCALAR_OVERFLOW]) {  // set on the device by the frame itself
+        snprintf(ctx->last_error, sizeof(ctx->last_error), "num_rendered %u exceeds list_capacity %u", n,
+                 ctx->h_scalars[LCGS_SCALAR_CAPACITY]);
         return LCGS_B200_ERR_CAPACITY;
     }
     return LCGS_B200_OK;
@@ -560,6 +573,35 @@ int lcgs_b200_read_image(lcgs_b200_ctx* ctx, const lcgs_b200_frame* fr, float* h
     LCGS_CUDA_CHECK(ctx, cudaMemcpyAsync(host_img, fr->target_img, (size_t)3 * fr->width * fr->height * sizeof(float),
                                          cudaMemcpyDeviceToHost, as_stream(stream)));
     return LCGS_B200_OK;
+}
+
+int lcgs_b200_read_image_rgb8(lcgs_b200_ctx* ctx, const lcgs_b200_frame* fr, uint8_t* host_rgb, lcgs_b200_stream stream)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, fr && host_rgb && fr->target_rgb8, "read_image_rgb8: null pointer");
+    LCGS_CUDA_CHECK(ctx, cudaMemcpyAsync(host_rgb, fr->target_rgb8, (size_t)3 * fr->width * fr->height, cudaMemcpyDeviceToHost,
+                                         as_stream(stream)));
+    return LCGS_B200_OK;
+}
+
+int lcgs_b200_scene_prepare(lcgs_b200_ctx* ctx, int P, const float* opacity, float* consts, lcgs_b200_stream stream)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, P >= 0 && (P == 0 || (opacity && consts)), "scene_prepare: bad arguments");
+    LCGS_REQUIRE(ctx, aligned(consts, 8), "scene_prepare: consts must be 8-byte aligned");
+    return launch_scene_prepare(ctx, P, opacity, consts, as_stream(stream));
+}
+
+int lcgs_b200_transpose_rgba8(lcgs_b200_ctx* ctx, int width, int height, const float* img_chw, uint8_t* rgba,
+                              lcgs_b200_stream stream)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, width > 0 && height > 0 && img_chw && rgba, "transpose_rgba8: bad arguments");
+    LCGS_REQUIRE(ctx, aligned(rgba, 4), "transpose_rgba8: rgba must be 4-byte aligned");
+    return launch_transpose_rgba8(ctx, width, height, img_chw, rgba, as_stream(stream));
 }
 
 // ---- multi-GPU: peer-writable output buffers (CUDA IPC) ---------------------------------------------
@@ -603,6 +645,15 @@ int lcgs_b200_peer_read(lcgs_b200_ctx* ctx, const void* dev_ptr, void* host_ptr,
     return LCGS_B200_OK;
 }
 
+int lcgs_b200_peer_read_async(lcgs_b200_ctx* ctx, const void* dev_ptr, void* host_ptr, size_t bytes, lcgs_b200_stream stream)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, dev_ptr && host_ptr, "peer_read_async: null pointer");
+    LCGS_CUDA_CHECK(ctx, cudaMemcpyAsync(host_ptr, dev_ptr, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    return LCGS_B200_OK;
+}
+
 int lcgs_b200_peer_close(lcgs_b200_ctx* ctx, void* dev_ptr)
 {
     int rc = enter(ctx);
@@ -617,6 +668,40 @@ int lcgs_b200_peer_free(lcgs_b200_ctx* ctx, void* dev_ptr)
     if (rc) return rc;
     LCGS_CUDA_CHECK(ctx, cudaFree(dev_ptr));
     return LCGS_B200_OK;
+}
+
+int lcgs_b200_peer_signal(lcgs_b200_ctx* ctx, uint32_t* flag, uint32_t value, lcgs_b200_stream stream)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, flag && aligned(flag, 4), "peer_signal: bad flag pointer");
+    return launch_peer_signal(ctx, flag, value, as_stream(stream));
+}
+
+int lcgs_b200_peer_wait(lcgs_b200_ctx* ctx, const uint32_t* flag, uint32_t value, uint32_t timeout_ms, lcgs_b200_stream stream)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, flag && aligned(flag, 4), "peer_wait: bad flag pointer");
+    return launch_peer_wait(ctx, flag, value, timeout_ms, as_stream(stream));
+}
+
+int lcgs_b200_peer_error(lcgs_b200_ctx* ctx, uint32_t* timed_out)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, timed_out, "peer_error: null pointer");
+    LCGS_CUDA_CHECK(ctx, cudaDeviceSynchronize());
+    LCGS_CUDA_CHECK(ctx, cudaMemcpy(timed_out, ctx->d_scalars + LCGS_SCALAR_PEER_TIMEOUTS, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return LCGS_B200_OK;
+}
+
+int lcgs_b200_checksum_u32(lcgs_b200_ctx* ctx, const void* data, size_t num_words, uint64_t* out, lcgs_b200_stream stream)
+{
+    int rc = enter(ctx);
+    if (rc) return rc;
+    LCGS_REQUIRE(ctx, out && aligned(out, 8) && (num_words == 0 || (data && aligned(data, 16))), "checksum: bad arguments");
+    return launch_checksum_u32(ctx, data, num_words, out, as_stream(stream));
 }
 
 int lcgs_b200_set_profiling(lcgs_b200_ctx* ctx, int enabled)

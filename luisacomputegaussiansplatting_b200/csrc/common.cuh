@@ -43,7 +43,7 @@ struct lcgs_b200_ctx {
     int          device     = 0;
     int          num_sms    = lcgs_b200::kNumSMs;
     char         last_error[256];
-    // device scalars: [0] num_rendered (instances), [1] overflow flag, [2..] tickets
+    // device scalars: [0] num_rendered (instances), [1] Gaussians touching a tile, [2..] tickets, [13] overflow flag
     uint32_t*    d_scalars  = nullptr;
     uint32_t*    h_scalars  = nullptr;  // pinned mirror
     // workspaces, grown geometrically and never shrunk (like ensure_*_temp_buffer,
@@ -52,6 +52,7 @@ struct lcgs_b200_ctx {
     lcgs_b200::Workspace sort_ws;     // histograms + look-back status + ping-pong pair buffer
     lcgs_b200::Workspace record_ws;   // packed per-Gaussian blend records
     lcgs_b200::Workspace order_ws;    // fused path: packed rects + compacted/sorted (depth, index) pairs + offsets
+    lcgs_b200::Workspace tile_order_ws;  // blend: tile ids, longest list first
     // per-stage timing
     int          profiling  = 0;
     cudaEvent_t  ev[16];
@@ -70,6 +71,9 @@ struct lcgs_b200_ctx {
 #define LCGS_SCALAR_SCAN_TICKET  2
 #define LCGS_SCALAR_SORT_TICKET  3   /* .. 3 + kMaxSortPasses - 1 */
 #define LCGS_SCALAR_DUP_TICKET   12
+#define LCGS_SCALAR_OVERFLOW     13  /* 1 iff the last frame's num_rendered exceeded its list_capacity (device-side test) */
+#define LCGS_SCALAR_CAPACITY     14  /* that frame's list_capacity (clamped to 2^32-1), written in-stream; = OVERFLOW + 1 */
+#define LCGS_SCALAR_PEER_TIMEOUTS 15  /* sticky: peer waits that gave up (lcgs_b200_peer_error) */
 #define LCGS_NUM_SCALARS         16
 
 #define LCGS_CUDA_CHECK(ctx, expr)                                                                   \
@@ -95,14 +99,14 @@ namespace lcgs_b200 {
 
 int ws_reserve(lcgs_b200_ctx* ctx, Workspace& ws, size_t bytes);
 
-// Tuning hook (lcgs_b200_debug_ablate): bits that make a kernel DROP one part of its work so that the
-// part's cost can be measured on the real frame.  Results are wrong while any bit is set; 0 in production.
-extern int g_ablate;
-constexpr int kAblateSortStores = 1, kAblateSortLookback = 2, kAblateDupHist = 4, kAblateDupStores = 8, kAblateDupGather = 16,
-              kAblateCompactHist = 32, kAblateCompactDepth = 64;
-// Not an ablation (results stay exact): take the emission kernel's general path -- integer division and owner search
-// by shuffle, otherwise only used for grids beyond gx * gx * gy >= 2^32 -- so that tests can cover it.
-constexpr int kDebugDupSlowPath = 128;
+// Geometry overrides by environment variable exist only in -DLCGS_TUNING builds (build.py --tuning, a separate
+// library used by scripts/tune_*.py); the production library always runs the measured defaults.
+#ifdef LCGS_TUNING
+int tuning_env_int(const char* name, int fallback);
+#define LCGS_TUNE_INT(name, fallback) ::lcgs_b200::tuning_env_int(name, fallback)
+#else
+#define LCGS_TUNE_INT(name, fallback) (fallback)
+#endif
 
 // stage launchers (one group per .cu); all enqueue on `s` and return an lcgs_b200_status
 int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b200_view_params* vp,
@@ -112,9 +116,9 @@ int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const
                         uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, const SortDigits* digits,
                         cudaStream_t s);
 struct SortedPairsU32;
-int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, int H, const SortedPairsU32& sorted,
-                                 const uint2* rects, uint64_t* keys, uint32_t* vals, size_t capacity, int row0,
-                                 const SortDigits* digits, cudaStream_t s);
+int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, int H, int num_rows,
+                                 const SortedPairsU32& sorted, const uint2* rects, uint64_t* keys, uint32_t* vals,
+                                 size_t capacity, int row0, const SortDigits* digits, cudaStream_t s);
 // digit layout of a prepared sort, for kernels that accumulate its histograms while producing the keys
 struct SortDigits {
     uint32_t* hist;  // [num_passes][1 << radix_bits], zeroed
@@ -155,7 +159,15 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
 int launch_ranges(lcgs_b200_ctx* ctx, const uint64_t* keys, size_t n_host, const uint32_t* d_n, size_t capacity,
                   uint32_t* ranges, int num_tiles, cudaStream_t s);
 int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32_t* ranges, const uint32_t* point_list,
-                 const float4* records, const uint32_t* d_num_rendered, float* img, int row0, int row1, cudaStream_t s);
+                 const float4* records, const uint32_t* d_num_rendered, float* img, uint8_t* rgb8, int row0, int row1,
+                 cudaStream_t s);
+int launch_transpose_rgba8(lcgs_b200_ctx* ctx, int W, int H, const float* img, uint8_t* rgba, cudaStream_t s);
+int launch_scene_prepare(lcgs_b200_ctx* ctx, int P, const float* opacity, float* consts, cudaStream_t s);
+int launch_tile_order(lcgs_b200_ctx* ctx, const uint32_t* ranges, int num_tiles, const uint32_t* d_num_rendered,
+                      size_t list_capacity, cudaStream_t s);
+int launch_peer_signal(lcgs_b200_ctx* ctx, uint32_t* flag, uint32_t value, cudaStream_t s);
+int launch_peer_wait(lcgs_b200_ctx* ctx, const uint32_t* flag, uint32_t value, uint32_t timeout_ms, cudaStream_t s);
+int launch_checksum_u32(lcgs_b200_ctx* ctx, const void* data, size_t num_words, uint64_t* out, cudaStream_t s);
 int launch_fill_u32(lcgs_b200_ctx* ctx, uint32_t* buf, size_t n, uint32_t v, cudaStream_t s);
 int launch_fill_u64(lcgs_b200_ctx* ctx, uint64_t* buf, size_t n, uint64_t v, cudaStream_t s);
 int launch_fill_f32(lcgs_b200_ctx* ctx, float* buf, size_t n, float v, cudaStream_t s);

@@ -22,6 +22,7 @@ struct PreprocessArgs {
     const float* rotq;
     const float* sh;
     const float* opacity;
+    const float2* alpha_consts;  // optional per-scene (power threshold, log2 opacity), lcgs_b200_scene_prepare
     float        scale_modifier;
     ViewParams   vp;
     uint32_t     gx, gy, row0, row1;
@@ -49,16 +50,29 @@ struct GlobalSh {
     __device__ __forceinline__ float operator()(int k, int c) const { return __ldg(p + k * 3 + c); }
 };
 
-__device__ __forceinline__ void write_record(float4* rec, const Splat2D& s, float op, const float* rgb)
+// (thr, l2op) = (alpha_threshold(opacity), log2f(opacity)): the two per-Gaussian constants of the alpha test
+__device__ __forceinline__ void write_record(float4* rec, const Splat2D& s, float thr, float l2op, const float* rgb)
 {
-    const float    thr = alpha_threshold(op);
     const float    a = -0.5f * s.conic[0], b = -s.conic[1], c = -0.5f * s.conic[2];
     const CullCoef k = cull_coef(s.px, s.py, a, b, c, thr);
     rec[0] = make_float4(s.px, s.py, a, b);
-    rec[1] = make_float4(c, thr, log2f(op), k.ry);  // the blend evaluates alpha as 2^(power*log2e + log2(opacity))
+    rec[1] = make_float4(c, thr, l2op, k.ry);  // the blend evaluates alpha as 2^(power*log2e + log2(opacity))
     rec[2] = make_float4(rgb[0], rgb[1], rgb[2], k.rx);
 }
 
+// The alpha-test constants depend on the opacity alone.  Computing the threshold is a binary64 search
+// (alpha_threshold(), ~25 % of the fused kernel's issue slots), so a caller that renders many frames of one
+// scene computes them once (lcgs_b200_scene_prepare) and passes them in lcgs_b200_scene::alpha_consts.
+__global__ void __launch_bounds__(256) scene_prepare_kernel(int P, const float* __restrict__ opacity, float2* __restrict__ consts)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float op = __ldg(opacity + i);
+    consts[i]      = make_float2(alpha_threshold(op), log2f(op));
+}
+
+// HAS_CONSTS: read (threshold, log2 opacity) from the per-scene array instead of deriving them from the opacity
+template <bool HAS_CONSTS>
 __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __grid_constant__ PreprocessArgs a)
 {
     // Every warp works on its own 32 Gaussians and its own slice of shared memory: no block-wide
@@ -72,14 +86,19 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
     float4* const  w_sh = s_sh + warp * 32 * kShRowPad;
 
     // ---- phase 1: geometry ----------------------------------------------------------------
-    float   px = 0.f, py = 0.f, pz = 0.f, op = 0.f;
+    float   px = 0.f, py = 0.f, pz = 0.f, thr = 0.f, l2op = 0.f;
     Splat2D s;
     s.tiles   = 0;
     bool need = false;
     if (i < a.P) {
         // opacity is only needed by Gaussians that touch a tile, but a predicated 4-byte load costs a
         // whole 32-byte sector per Gaussian; unconditionally the warp reads 128 contiguous bytes
-        op = __ldg(a.opacity + i);
+        if (HAS_CONSTS) {
+            const float2 k = __ldg(a.alpha_consts + i);
+            thr = k.x; l2op = k.y;
+        } else {
+            l2op = __ldg(a.opacity + i);  // the opacity itself until phase 3
+        }
         px = __ldg(a.pos + 3 * i);
         py = __ldg(a.pos + 3 * i + 1);
         pz = __ldg(a.pos + 3 * i + 2);
@@ -159,7 +178,11 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
             a.color[3 * i + 1] = rgb[1];
             a.color[3 * i + 2] = rgb[2];
         }
-        write_record(a.records + (size_t)i * kRecordFloat4s, s, op, rgb);
+        if (!HAS_CONSTS) {
+            thr  = alpha_threshold(l2op);
+            l2op = log2f(l2op);
+        }
+        write_record(a.records + (size_t)i * kRecordFloat4s, s, thr, l2op, rgb);
     }
 }
 
@@ -245,7 +268,8 @@ __global__ void __launch_bounds__(256)
     s.conic[1] = conic[3 * i + 1];
     s.conic[2] = conic[3 * i + 2];
     const float rgb[3] = { color[3 * i], color[3 * i + 1], color[3 * i + 2] };
-    write_record(records + (size_t)i * kRecordFloat4s, s, opacity[i], rgb);
+    const float op = opacity[i];
+    write_record(records + (size_t)i * kRecordFloat4s, s, alpha_threshold(op), log2f(op), rgb);
 }
 
 // ---- launchers -------------------------------------------------------------------------------
@@ -260,6 +284,7 @@ int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const
     PreprocessArgs a;
     a.P = P; a.sh_deg = sc->sh_deg;
     a.pos = sc->pos; a.scale = sc->scale; a.rotq = sc->rotq; a.sh = sc->sh; a.opacity = sc->opacity;
+    a.alpha_consts = reinterpret_cast<const float2*>(sc->alpha_consts);
     a.scale_modifier = sc->scale_modifier;
     static_assert(sizeof(ViewParams) == sizeof(lcgs_b200_view_params), "view params layout");
     memcpy(&a.vp, vp, sizeof(ViewParams));
@@ -269,7 +294,16 @@ int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const
     a.row1 = fr->tile_row_end < 0 ? a.gy : (uint32_t)fr->tile_row_end;
     a.means_2d = fr->means_2d; a.depth = fr->depth; a.conic = fr->conic; a.color = fr->color;
     a.radii = fr->radii; a.tiles = fr->tiles_touched; a.records = records; a.rects = rects;
-    preprocess_fused_kernel<<<div_up(P, kPreThreads), kPreThreads, 0, s>>>(a);
+    if (a.alpha_consts) preprocess_fused_kernel<true><<<div_up(P, kPreThreads), kPreThreads, 0, s>>>(a);
+    else preprocess_fused_kernel<false><<<div_up(P, kPreThreads), kPreThreads, 0, s>>>(a);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+int launch_scene_prepare(lcgs_b200_ctx* ctx, int P, const float* opacity, float* consts, cudaStream_t s)
+{
+    if (P <= 0) return LCGS_B200_OK;
+    scene_prepare_kernel<<<div_up(P, 256), 256, 0, s>>>(P, opacity, reinterpret_cast<float2*>(consts));
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }

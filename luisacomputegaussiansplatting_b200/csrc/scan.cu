@@ -136,13 +136,13 @@ __global__ void __launch_bounds__(kScanThreads)
     scan_compact_kernel(const uint32_t* __restrict__ tiles_touched, const float* __restrict__ depth, uint32_t n,
                         uint32_t num_tiles, uint32_t* __restrict__ offsets, uint32_t* __restrict__ ckeys,
                         uint32_t* __restrict__ cvals, unsigned long long* status_sum, unsigned long long* status_cnt,
-                        uint32_t* ticket, uint32_t* d_total, uint32_t* d_count, const __grid_constant__ SortDigits digits, int ablate)
+                        uint32_t* ticket, uint32_t* d_total, uint32_t* d_count, const __grid_constant__ SortDigits digits, int vec_ok)
 {
     // digit histograms of the depth keys this CTA compacts (the depth sort then skips its histogram kernel)
     __shared__ uint32_t s_hist[4 * 512];
     // the CTA's compacted (key, index) pairs, staged so that they leave as two coalesced runs
     __shared__ uint32_t s_key[kCompactTile], s_idx[kCompactTile];
-    const bool          do_hist = digits.hist != nullptr && !(ablate & kAblateCompactHist);
+    const bool          do_hist = digits.hist != nullptr;
     const int           nbins   = do_hist ? (digits.num_passes << digits.radix_bits) : 0;
     for (int k = threadIdx.x; k < nbins; k += kScanThreads) s_hist[k] = 0u;
     __shared__ uint32_t s_tile;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kScanThreads)
     // are requested up front for every item (4 B each), not one dependent load per touching Gaussian
     const uint32_t e0 = tile * kCompactTile + tid * kCompactItems;
     uint32_t       v[kCompactItems], dk[kCompactItems];
-    if (e0 + kCompactItems <= n) {
+    if (vec_ok && e0 + kCompactItems <= n) {
         const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(tiles_touched + e0));
         const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(tiles_touched + e0) + 1);
         const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(depth + e0));
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kScanThreads)
         sum += v[k];
         out[k] = sum;
         if (v[k] > 0u) {
-            s_key[slot] = ((ablate & kAblateCompactDepth) ? (e0 + k) * 2654435761u : dk[k]) - kDepthKeyBase;
+            s_key[slot] = dk[k] - kDepthKeyBase;
             s_idx[slot] = e0 + k;
             slot++;
         }
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kScanThreads)
         *d_total = base_sum + tot.a;
         *d_count = base_cnt + tot.b;
     }
-    if (e0 + kCompactItems <= n) {
+    if (vec_ok && e0 + kCompactItems <= n) {
         reinterpret_cast<uint4*>(offsets + e0)[0] = make_uint4(base_sum + out[0], base_sum + out[1], base_sum + out[2], base_sum + out[3]);
         reinterpret_cast<uint4*>(offsets + e0)[1] = make_uint4(base_sum + out[4], base_sum + out[5], base_sum + out[6], base_sum + out[7]);
     } else {
@@ -241,8 +241,8 @@ int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const
         LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s));
         return LCGS_B200_OK;
     }
-    LCGS_REQUIRE(ctx, ((((uintptr_t)tiles_touched) | ((uintptr_t)offsets) | ((uintptr_t)depth)) & 15) == 0,
-                 "scan: tiles_touched / point_offsets / depth must be 16-byte aligned");
+    // 16-byte aligned buffers (any cudaMalloc'ed array) take the vector path, sub-allocated ones the scalar one
+    const int vec_ok = ((((uintptr_t)tiles_touched) | ((uintptr_t)offsets) | ((uintptr_t)depth)) & 15) == 0;
     const uint32_t tiles = (uint32_t)(((size_t)P + kCompactTile - 1) / kCompactTile);
     int            rc    = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * 2 * sizeof(unsigned long long));
     if (rc) return rc;
@@ -251,7 +251,7 @@ int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
     auto* st = (unsigned long long*)ctx->scan_ws.ptr;
     scan_compact_kernel<<<tiles, kScanThreads, 0, s>>>(tiles_touched, depth, (uint32_t)P, tiles, offsets, ckeys, cvals, st,
-                                                       st + tiles, ticket, d_total, d_count, dg, g_ablate);
+                                                       st + tiles, ticket, d_total, d_count, dg, vec_ok);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }

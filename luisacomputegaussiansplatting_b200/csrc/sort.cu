@@ -29,9 +29,8 @@ constexpr uint32_t kStatusAggregate = 1u << 30;
 constexpr uint32_t kStatusInclusive = 2u << 30;
 constexpr uint32_t kStatusValueMask = (1u << 30) - 1u;
 constexpr int      kLookbackWindow  = 8;
-// onesweep_pass_kernel flags.  The Ablate* bits (lcgs_b200_debug_ablate, tuning only) produce WRONG results:
-// they drop one phase so that its share of the pass can be measured.
-constexpr int kSweepSkipIfTrivial = 1, kSweepAblateStores = 2, kSweepAblateLookback = 4;
+// onesweep_pass_kernel flags
+constexpr int kSweepSkipIfTrivial = 1;
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
 {
@@ -51,6 +50,13 @@ __device__ __forceinline__ uint32_t atom_shared_add(uint32_t addr, uint32_t v)
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
     return old;
 }
+
+// 4-byte asynchronous copy global -> shared (LDGSTS): the value never occupies a register
+__device__ __forceinline__ void cp_async_u32(uint32_t smem_addr, const uint32_t* gptr)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ size_t resolve_n(size_t n_host, const uint32_t* d_n, size_t capacity)
 {
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                          const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
                          const uint32_t* __restrict__ d_n, size_t capacity, const uint32_t* __restrict__ hist /* [RADIX] */,
                          uint32_t* status /* [tiles][RADIX] */, uint32_t* ticket, int shift, uint32_t mask,
-                         int flags /* kSweep* */, unsigned long long* dbg /* optional phase timers, LCGS_SORT_DEBUG=1 */)
+                         int flags /* kSweep* */)
 {
     constexpr int RADIX = 1 << RBITS;
     constexpr int WARPS = THREADS / 32;
@@ -204,12 +210,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const uint32_t num_tiles = (uint32_t)((n + TILE - 1) / TILE);
     const uint32_t q0        = warp * (ITEMS * 32) + lane;  // warp-striped: item j sits at q0 + 32*j
     const bool     is_digit  = tid < RADIX;
+    const uint32_t  s_vals_addr = (uint32_t)__cvta_generic_to_shared(s_vals);
     uint32_t* const my_hist  = s_wh + warp * RADIX;
     const uint32_t  my_hist_addr = (uint32_t)__cvta_generic_to_shared(my_hist);
     // every key has digit 0 in this pass (the top bits of the depth keys): the pass is the identity
     // permutation; the consumers of the sorted list make the same test and read this pass's input
     if ((flags & kSweepSkipIfTrivial) && __ldg(hist) == (uint32_t)n) return;
-    const bool ablate_stores = flags & kSweepAblateStores, ablate_lookback = flags & kSweepAblateLookback;  // tuning only
 
     auto digit_of = [&](KeyT k) -> uint32_t { return HI ? key_digit_hi(k, shift, mask) : key_digit(k, shift, mask); };
     auto tile_valid = [&](uint32_t t) -> uint32_t {
@@ -245,14 +251,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     };
     load_keys(tile);
 
-    long long t_prev = dbg ? clock64() : 0;
-    auto      lap    = [&](int phase) {
-        if (dbg && tid == 0) {
-            const long long t = clock64();
-            atomicAdd(dbg + phase, (unsigned long long)(t - t_prev));
-            t_prev = t;
-        }
-    };
     // One tile; `full_c` makes "every slot of the tile holds a pair" a compile-time fact (all tiles but the last),
     // which removes the per-item bounds predicates and the extra ballot for the invalid flag.
     auto process_tile = [&](auto full_c, const uint32_t nvalid) {
@@ -276,17 +274,16 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             rd[j]  = (d << 16) | (before + __popc(lower));
         }
         __syncthreads();
-        lap(0);  // wait for keys + rank
         const uint32_t next_tile = s_ticket[1];
 
-        // ---- the values are requested now and scattered next to their keys after the digit scan ------
-        uint32_t        val[ITEMS];
+        // The values never pass through registers: once an item's slot is known (the scatter below), its
+        // value is copied global -> shared memory asynchronously (LDGSTS, 4 bytes) straight into that slot,
+        // and the copies are waited for behind the look-back.  Holding ITEMS values in registers from here
+        // to the scatter made the 256 x 20 geometry spill at its 128-register budget.
         const uint32_t* vsrc = vals_in + (size_t)tile * TILE + q0;
-#pragma unroll
-        for (int j = 0; j < ITEMS; j++) val[j] = (full || q0 + 32 * j < nvalid) ? __ldg(vsrc + 32 * j) : 0u;
 
         // ---- per digit (thread d): tile histogram, early publish, first look-back window ---------
-        constexpr bool  kCntInRegs = WARPS <= 16;  // otherwise re-read the counters instead of holding them
+        constexpr bool  kCntInRegs = WARPS <= 16 && ITEMS * (int)sizeof(KeyT) < 160;  // otherwise re-read the counters instead of holding them
         uint32_t        tile_count = 0, scan_incl = 0;
         uint32_t        cnt[kCntInRegs ? WARPS : 1];
         uint32_t        st[kLookbackWindow];
@@ -329,7 +326,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             }
         }
         __syncthreads();
-        lap(1);  // digit prefix + scan
 
         // ---- scatter keys and values into shared memory in tile-sorted order ---------------------
 #pragma unroll
@@ -337,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             if (full || q0 + 32 * j < nvalid) {
                 const uint32_t slot = (rd[j] & 0xFFFFu) + my_hist[rd[j] >> 16];
                 s_keys[slot] = key[j];
-                s_vals[slot] = val[j];
+                cp_async_u32(s_vals_addr + slot * 4u, vsrc + 32 * j);
             }
         }
         // this warp's counters are free again: clear them for its next tile (only the warp itself touches
@@ -347,12 +343,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         for (int k = lane; k < RADIX; k += 32) my_hist[k] = 0u;
         // the key registers are free: request the next tile's keys behind the look-back and the write-out
         load_keys(next_tile);
-        lap(2);  // scatter
 
         // ---- decoupled look-back: consume the window requested above, then further windows ---------
         if (is_digit) {
             uint32_t prefix = 0;
-            bool     more   = tile > 0 && !ablate_lookback;
+            bool     more   = tile > 0;
             while (more) {
 #pragma unroll
                 for (int k = 0; k < kLookbackWindow; k++) {
@@ -374,24 +369,20 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             st_relaxed_u32(my_status, kStatusInclusive | ((prefix + tile_count) & kStatusValueMask));
             s_base[tid] = bin_base + prefix - tile_start;
         }
-        lap(3);  // thread 0's own look-back
-
+        cp_async_wait_all();  // this thread's value copies have landed; the barrier publishes everybody's
         __syncthreads();
-        lap(4);  // wait for the slowest digit's look-back
 
         // ---- coalesced write-out of keys and values ------------------------------------------------
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             const uint32_t q = tid + j * THREADS;
-            if ((full || q < nvalid) && !ablate_stores) {
+            if (full || q < nvalid) {
                 const KeyT     k   = s_keys[q];
                 const uint32_t dst = s_base[digit_of(k)] + q;
                 keys_out[dst]      = k;
                 vals_out[dst]      = s_vals[q];
             }
         }
-        lap(5);  // write-out
-        if (dbg && tid == 0) atomicAdd(dbg + 10, 1ull);
         tile = next_tile;
     };
     while (tile < num_tiles) {
@@ -421,7 +412,7 @@ __global__ void __launch_bounds__(256)
 template <typename KeyT>
 struct SweepVariant {
     using Kernel = void (*)(const KeyT*, KeyT*, const uint32_t*, uint32_t*, size_t, const uint32_t*, size_t, const uint32_t*,
-                            uint32_t*, uint32_t*, int, uint32_t, int, unsigned long long*);
+                            uint32_t*, uint32_t*, int, uint32_t, int);
     Kernel      kernel[2];  // [0] digit anywhere below bit 32 or across it, [1] digit in the upper word (64-bit keys)
     int         threads, tile, radix_bits, blocks_per_sm;
     size_t      smem;
@@ -442,6 +433,12 @@ static const SweepVariant<unsigned long long> kSweep64[] = {
     LCGS_SWEEP64(256, 20, 7, 2, false),  // 2: 7-bit digits, ballot ranking, 5120-pair tiles: <= 14 key bits (fused flow)
     LCGS_SWEEP64(256, 12, 7, 4, false),  // 3: same, 3072-pair tiles, 4 CTAs/SM
     LCGS_SWEEP64(512, 8, 7, 2, true),    // 4: 7-bit digits, MATCH.ANY ranking (the earlier default)
+#ifdef LCGS_TUNING
+    LCGS_SWEEP64(256, 16, 7, 3, false),  // 5: 4096-pair tiles, 3 CTAs/SM (85 registers)
+    LCGS_SWEEP64(256, 24, 7, 2, false),  // 6: 6144-pair tiles
+    LCGS_SWEEP64(384, 14, 7, 2, false),  // 7: 5376-pair tiles, 12 warps per CTA
+    LCGS_SWEEP64(512, 10, 7, 2, false),  // 8: 5120-pair tiles, 16 warps per CTA (64 registers)
+#endif
 };
 // 32-bit depth keys of the per-Gaussian sort
 static const SweepVariant<uint32_t> kSweep32[] = {
@@ -472,13 +469,8 @@ struct SweepTable<uint32_t> {
 template <typename KeyT>
 static int sweep_variant_index(int bits)
 {
-    static int env_idx = -2;
-    if (env_idx == -2) {
-        env_idx       = -1;
-        const char* e = getenv(SweepTable<KeyT>::env());
-        if (e && atoi(e) >= 0 && atoi(e) < SweepTable<KeyT>::count()) env_idx = atoi(e);
-    }
-    if (env_idx >= 0) return env_idx;
+    const int env_idx = LCGS_TUNE_INT(SweepTable<KeyT>::env(), -1);  // -1 outside -DLCGS_TUNING builds
+    if (env_idx >= 0 && env_idx < SweepTable<KeyT>::count()) return env_idx;
     // measured: two 7-bit ballot passes for up to 14 tile bits (256 x 20, 2 CTAs/SM); two 9-bit ballot passes up to
     // 18 bits (the 8K frame's 17 tile bits: 4.8 ms vs 5.4 ms with MATCH); MATCH ranking for longer keys
     // (the reference flow's 45 bits = 5 passes: 1.11 ms vs 1.17 ms with ten ballots per item)
@@ -607,25 +599,6 @@ static int launch_sort_t(lcgs_b200_ctx* ctx, const SortPlan<KeyT>& plan, const K
     }
     const size_t   max_ctas     = (size_t)ctx->num_sms * var.blocks_per_sm;
     const unsigned sweep_blocks = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-    // LCGS_SORT_DEBUG=1: accumulate per-phase clock64() deltas of thread 0 of every CTA (tuning only)
-    static unsigned long long* dbg      = nullptr;
-    static int                 dbg_init = 0;
-    if (!dbg_init) {
-        dbg_init = 1;
-        if (getenv("LCGS_SORT_DEBUG")) {
-            LCGS_CUDA_CHECK(ctx, cudaMalloc(&dbg, 16 * sizeof(unsigned long long)));
-            LCGS_CUDA_CHECK(ctx, cudaMemset(dbg, 0, 16 * sizeof(unsigned long long)));
-        }
-    }
-    if (dbg && getenv("LCGS_SORT_DEBUG_PRINT")) {
-        unsigned long long h[16];
-        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        cudaMemset(dbg, 0, sizeof(h));
-        if (h[10])
-            fprintf(stderr, "[sort dbg] tiles %llu cycles/tile: rank %llu prefix %llu scatter %llu lookback(t0) %llu lb-wait %llu write %llu\n",
-                    h[10], h[0] / h[10], h[1] / h[10], h[2] / h[10], h[3] / h[10], h[4] / h[10], h[5] / h[10]);
-    }
-    const int ablate = ((g_ablate & kAblateSortStores) ? kSweepAblateStores : 0) | ((g_ablate & kAblateSortLookback) ? kSweepAblateLookback : 0);
     const KeyT*     src_k = kin;
     const uint32_t* src_v = vals_in;
     for (int p = 0; p < info.num_passes; p++) {
@@ -646,7 +619,7 @@ static int launch_sort_t(lcgs_b200_ctx* ctx, const SortPlan<KeyT>& plan, const K
                                                               plan.hist + (size_t)p * radix,
                                                               plan.status + (size_t)p * tiles * radix, ticket + p,
                                                               info.shift[p], info.mask[p],
-                                                              ((last && skip_trivial_last) ? kSweepSkipIfTrivial : 0) | ablate, dbg);
+                                                              (last && skip_trivial_last) ? kSweepSkipIfTrivial : 0);
         LCGS_CUDA_CHECK(ctx, cudaGetLastError());
         src_k = dst_k;
         src_v = dst_v;

@@ -111,22 +111,64 @@ def gather_strips(img: torch.Tensor, bands: Sequence[Tuple[int, int]], height: i
 # --------------------------------------------------------------------------------------------------
 
 class PeerFrameRing:
-    """`slots` planar [3,H,W] float32 images in ONE buffer on rank `dst` that every rank can write over
-    NVLink (lcgs.PeerBuffer).  A rank renders straight into `ptr(slot)` -- or, for tile-row sharding, all
-    ranks render their bands into the same slot -- so the blend kernel's stores are the gather.  After the
-    writers' streams have finished and the ranks have met at a barrier, dst reads the frames."""
+    """`slots` frames in ONE buffer on rank `dst` that every rank can write over NVLink (lcgs.PeerBuffer).
+    A slot is a planar [3,H,W] float32 image, optionally followed by the uint8 HWC image the app saves
+    (`rgb8=True`).  A rank renders straight into `ptr(slot)` -- or, for tile-row sharding, all ranks render
+    their bands into the same slot -- so the blend kernel's stores are the gather.
 
-    def __init__(self, device, width: int, height: int, slots: int, dst: int = 0, group=None):
+    Two ways to hand frames over:
+      * batch:  `complete()` (stream sync + barrier), dst reads, `release()` (barrier);
+      * stream: per-slot 32-bit sequence flags inside the buffer (`ready`: written by the renderer after its frame,
+        polled by dst; `consumed`: written by dst after it has read the slot, polled by the renderer before it
+        overwrites the slot), all in stream order on the devices -- no host synchronisation between frames
+        (`signal_ready` / `wait_ready` / `signal_consumed` / `wait_consumed`).  For tile-row sharding every
+        writer has its own ready flag per slot (`writer`)."""
+
+    def __init__(self, device, width: int, height: int, slots: int, dst: int = 0, group=None, rgb8: bool = False,
+                 writers: int = 1):
         from . import lcgs
 
+        self.device = device
         self.W, self.H, self.slots, self.dst, self.group = width, height, slots, dst, group
-        self.frame_bytes = 3 * width * height * 4
-        self.buf = lcgs.PeerBuffer(device, self.frame_bytes * slots, owner=dst, group=group)
+        self.img_bytes = 3 * width * height * 4
+        self.rgb8_bytes = ((3 * width * height + 255) // 256) * 256 if rgb8 else 0
+        self.frame_bytes = self.img_bytes + self.rgb8_bytes          # a multiple of 4 (and of 16 for W*H % 4 == 0)
+        self.frame_bytes = ((self.frame_bytes + 255) // 256) * 256
+        self.writers = writers
+        self.flags_offset = self.frame_bytes * slots
+        # [slots][writers] ready words, then [slots] consumed words
+        self.buf = lcgs.PeerBuffer(device, self.flags_offset + 4 * slots * (writers + 1) + 256, owner=dst, group=group)
 
     def ptr(self, slot: int) -> int:
         assert 0 <= slot < self.slots
         return self.buf.ptr + slot * self.frame_bytes
 
+    def rgb8_ptr(self, slot: int) -> int:
+        assert self.rgb8_bytes
+        return self.ptr(slot) + self.img_bytes
+
+    def _ready_ptr(self, slot: int, writer: int = 0) -> int:
+        return self.buf.ptr + self.flags_offset + 4 * (slot * self.writers + writer)
+
+    def _consumed_ptr(self, slot: int) -> int:
+        return self.buf.ptr + self.flags_offset + 4 * (self.slots * self.writers + slot)
+
+    # ---- stream-ordered hand-over ----
+    def signal_ready(self, slot: int, seq: int, writer: int = 0, stream=None):
+        """Renderer: frame number `seq` (1, 2, ...) of this slot is complete once the stream gets here."""
+        self.device.peer_signal(self._ready_ptr(slot, writer), seq, stream)
+
+    def wait_ready(self, slot: int, seq: int, writer: int = 0, stream=None, timeout_ms: int = 5000):
+        self.device.peer_wait(self._ready_ptr(slot, writer), seq, timeout_ms, stream)
+
+    def signal_consumed(self, slot: int, seq: int, stream=None):
+        """dst: frame `seq` of this slot has been read; the slot may be overwritten."""
+        self.device.peer_signal(self._consumed_ptr(slot), seq, stream)
+
+    def wait_consumed(self, slot: int, seq: int, stream=None, timeout_ms: int = 5000):
+        self.device.peer_wait(self._consumed_ptr(slot), seq, timeout_ms, stream)
+
+    # ---- batch hand-over ----
     def complete(self):
         """All frames enqueued so far (on every rank) are visible on dst when this returns."""
         torch.cuda.synchronize()
@@ -165,14 +207,17 @@ def render_sweep_view_sharded_peer(render_view_into: Callable[[int, int], None],
 
 
 def render_frame_tile_row_sharded_peer(render_band_into: Callable[[int, int, int], None], height: int, ring: PeerFrameRing,
-                                       slot: int = 0, weights: Optional[Sequence[float]] = None):
+                                       slot: int = 0, weights: Optional[Sequence[float]] = None,
+                                       bands: Optional[Sequence[Tuple[int, int]]] = None):
     """Tile-row sharding with the gather fused into the render: every rank renders its band of tile rows
     directly into the SAME image (slot `slot` of `ring`) on the destination rank.
     `render_band_into(r0, r1, ptr)` enqueues the band [r0, r1) with target pointer `ptr`.
     Returns (assembled host image on dst / None, bands)."""
     world = dist.get_world_size(ring.group)
     rank = dist.get_rank(ring.group)
-    bands = split_tile_rows((height + 15) // 16, world, weights)
+    if bands is None:
+        bands = split_tile_rows((height + 15) // 16, world, weights)
+    assert len(bands) == world
     r0, r1 = bands[rank]
     if r1 > r0:
         render_band_into(r0, r1, ring.ptr(slot))
@@ -216,13 +261,15 @@ def render_sweep_view_sharded(render_view: Callable[[int], torch.Tensor], num_vi
 
 
 def render_frame_tile_row_sharded(render_band: Callable[[int, int], torch.Tensor], height: int,
-                                  weights: Optional[Sequence[float]] = None, dst: int = 0, group=None):
+                                  weights: Optional[Sequence[float]] = None, dst: int = 0, group=None,
+                                  bands: Optional[Sequence[Tuple[int, int]]] = None):
     """Render one frame split by tile rows: `render_band(r0, r1)` returns this rank's [3,H,W] image
     with its band rendered.  Returns (assembled image on dst / None, bands)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     gy = (height + 15) // 16
-    bands = split_tile_rows(gy, world, weights)
+    if bands is None:
+        bands = split_tile_rows(gy, world, weights)
     r0, r1 = bands[rank]
     img = render_band(r0, r1)
     return gather_strips(img, bands, height, dst=dst, group=group), bands

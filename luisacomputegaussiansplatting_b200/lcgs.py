@@ -130,6 +130,25 @@ class Device:
         self.check(self.lib.lcgs_b200_sort_breakdown(self.ctx, C.byref(h), C.byref(p), C.byref(k)))
         return dict(histogram_ms=h.value, passes_ms=p.value, num_passes=k.value)
 
+    # ---- multi-GPU flow control (device-side sequence flags in a peer buffer) and the consumer's checksum ----
+    def peer_signal(self, flag_ptr: int, value: int, stream: Optional[torch.cuda.Stream] = None):
+        self.check(self.lib.lcgs_b200_peer_signal(self.ctx, C.c_void_p(int(flag_ptr)), int(value) & 0xFFFFFFFF,
+                                                  _stream_handle(stream)))
+
+    def peer_wait(self, flag_ptr: int, value: int, timeout_ms: int = 5000, stream: Optional[torch.cuda.Stream] = None):
+        self.check(self.lib.lcgs_b200_peer_wait(self.ctx, C.c_void_p(int(flag_ptr)), int(value) & 0xFFFFFFFF, int(timeout_ms),
+                                                _stream_handle(stream)))
+
+    def peer_timeouts(self) -> int:
+        n = C.c_uint32()
+        self.check(self.lib.lcgs_b200_peer_error(self.ctx, C.byref(n)))
+        return int(n.value)
+
+    def checksum_u32(self, data_ptr: int, num_words: int, out: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
+        """out: one int64 device element = wrap-around sum of the 32-bit words at data_ptr."""
+        self.check(self.lib.lcgs_b200_checksum_u32(self.ctx, C.c_void_p(int(data_ptr)), int(num_words), out.data_ptr(),
+                                                   _stream_handle(stream)))
+
     def num_rendered(self, stream: Optional[torch.cuda.Stream] = None) -> int:
         n = C.c_int()
         self.check(self.lib.lcgs_b200_num_rendered(self.ctx, _stream_handle(stream), C.byref(n)))
@@ -346,6 +365,16 @@ class GSTileSplatter:
 # fused frame renderer (what the app's loop does, app/main.cpp:266-308)
 # --------------------------------------------------------------------------------------------------
 
+def transpose_rgba8(device: Device, img_chw: torch.Tensor, width: int, height: int, out: Optional[torch.Tensor] = None,
+                    stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """Display::_transpose_shader (app/display.cpp:30-39): planar float image -> [H, W, 4] RGBA8 framebuffer."""
+    if out is None:
+        out = torch.empty((height, width, 4), dtype=torch.uint8, device=img_chw.device)
+    device.check(device.lib.lcgs_b200_transpose_rgba8(device.ctx, int(width), int(height), _ptr(img_chw), _ptr(out),
+                                                      _stream_handle(stream)))
+    return out
+
+
 class PeerBuffer:
     """Device memory on the `owner` rank that every rank of the process group can write with plain stores
     over NVLink (lcgs_b200_peer_alloc / _open: CUDA IPC + peer access).  Passed as a render target, the
@@ -389,7 +418,11 @@ class Renderer:
 
     def __init__(self, device: Device, pos, scale, rotq, sh, opacity, width: int, height: int,
                  list_capacity: int = 20_000_000, sh_deg: int = 3, scale_modifier: float = 1.0,
-                 bg_color=(0.0, 0.0, 0.0), tile_rows=(0, -1), keep_intermediates: bool = True):
+                 bg_color=(0.0, 0.0, 0.0), tile_rows=(0, -1), keep_intermediates: bool = True,
+                 rgb8: bool = False, prepare_scene: bool = True):
+        """rgb8: the blend kernel also writes the app's uint8 HWC image (main.cpp:322-337) into `self.rgb8`.
+        prepare_scene: compute the per-scene alpha-test constants once (lcgs_b200_scene_prepare) instead of
+        deriving them from the opacity in every frame; call `scene_changed()` after modifying `opacity`."""
         self.device = device
         dev = device.torch_device
 
@@ -419,12 +452,14 @@ class Renderer:
         self.vals_unsorted = z(self.capacity, torch.int32)
         self.keys = z(self.capacity, torch.int64)
         self.vals = z(self.capacity, torch.int32)
-        self.ranges = z(2 * max(self.num_tiles, 1), torch.int32)
+        self.ranges = z(2 * max(self.gx * self.gy, 1), torch.int32)  # sized for the whole frame: bands can be re-cut
         self.img = z(3 * self.W * self.H, torch.float32)
         self.radii = z(P, torch.int32)
+        self.rgb8 = torch.zeros(3 * self.W * self.H, dtype=torch.uint8, device=dev) if rgb8 else None
+        self.alpha_consts = z(2 * P, torch.float32) if prepare_scene else None
 
         self.c_scene = _capi.Scene(P, int(sh_deg), _ptr(self.pos), _ptr(self.scale), _ptr(self.rotq), _ptr(self.sh),
-                                   _ptr(self.opacity), float(scale_modifier))
+                                   _ptr(self.opacity), float(scale_modifier), _ptr(self.alpha_consts))
         f = self.c_frame = _capi.Frame()
         f.width, f.height = self.W, self.H
         f.bg_color[:] = [float(x) for x in bg_color]
@@ -436,9 +471,23 @@ class Renderer:
         f.ranges, f.list_capacity = _ptr(self.ranges), self.capacity
         f.target_img, f.radii = _ptr(self.img), _ptr(self.radii)
         f.tile_row_begin, f.tile_row_end = r0, r1
+        f.target_rgb8 = _ptr(self.rgb8)
         device.reserve(P, self.capacity)
-        self._graph = None
-        self._graph_vp = None
+        self.scene_changed()
+
+    def set_tile_rows(self, r0: int, r1: int):
+        """Render tile rows [r0, r1) from the next frame on (tile-row sharding: bands re-balanced between frames)."""
+        assert 0 <= r0 <= r1 <= self.gy
+        self.tile_rows = (r0, r1)
+        self.num_tiles = self.gx * (r1 - r0)
+        self.c_frame.tile_row_begin, self.c_frame.tile_row_end = r0, r1
+
+    def scene_changed(self, stream: Optional[torch.cuda.Stream] = None):
+        """Refresh the per-scene constants derived from `opacity` (no-op without prepare_scene)."""
+        if self.alpha_consts is not None:
+            d = self.device
+            d.check(d.lib.lcgs_b200_scene_prepare(d.ctx, self.P, _ptr(self.opacity), _ptr(self.alpha_consts),
+                                                  _stream_handle(stream)))
 
     def nbytes_scene(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.pos, self.scale, self.rotq, self.sh, self.opacity))
@@ -458,16 +507,29 @@ class Renderer:
         d = self.device
         d.check(d.lib.lcgs_b200_read_image(d.ctx, C.byref(self.c_frame), host_img.data_ptr(), _stream_handle(stream)))
 
+    def read_image_rgb8(self, host_rgb: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
+        """Enqueue the D2H copy of the fused uint8 HWC image (3*W*H bytes) into pinned host memory."""
+        d = self.device
+        d.check(d.lib.lcgs_b200_read_image_rgb8(d.ctx, C.byref(self.c_frame), host_rgb.data_ptr(), _stream_handle(stream)))
+
+    def set_target_rgb8(self, rgb: Optional[torch.Tensor]):
+        assert rgb is None or (rgb.numel() == 3 * self.W * self.H and rgb.dtype == torch.uint8)
+        self.rgb8 = rgb
+        self.c_frame.target_rgb8 = _ptr(rgb)
+
     def set_target(self, img: torch.Tensor):
         """Render the following frames into another planar [3*H*W] float32 device buffer."""
         assert img.numel() == 3 * self.W * self.H and img.dtype == torch.float32
         self.img = img
         self.c_frame.target_img = _ptr(img)
 
-    def set_target_ptr(self, ptr: int):
+    def set_target_ptr(self, ptr: int, rgb8_ptr: Optional[int] = None):
         """Render the following frames into raw device memory (e.g. a slot of a PeerBuffer on another GPU):
-        a planar [3*H*W] float32 image at `ptr`.  `image()` keeps referring to the local buffer."""
+        a planar [3*H*W] float32 image at `ptr` (and, optionally, the uint8 HWC image at `rgb8_ptr`).
+        `image()` keeps referring to the local buffer."""
         self.c_frame.target_img = C.c_void_p(int(ptr))
+        if rgb8_ptr is not None:
+            self.c_frame.target_rgb8 = C.c_void_p(int(rgb8_ptr)) if rgb8_ptr else None
 
     def read_num_rendered_async(self, host_count: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
         """Enqueue a copy of the last enqueued frame's num_rendered into a pinned int32 host tensor."""

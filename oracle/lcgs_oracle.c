@@ -673,6 +673,15 @@ ORC_API long orc_exp_monotonicity_violations(float lo, float hi)
  * which is the reference's -0.5*(con.x*dx*dx + con.z*dy*dy) - con.y*dx*dy.
  * img is planar CHW; rows [row0*16, min(H,row1*16)) are written, tile ids are band-local.
  * n_examined (optional, W*H) receives the reference's `contributor` counter. */
+/* Totals of the last orc_blend call, for the blend roofline of SURVEY.md 8d: E = (pixel, list entry) pairs examined
+ * (the reference's `contributor` counter, shader.cpp:219,252), E_alpha = pairs that passed the alpha test,
+ * E_contrib = pairs that were blended into the pixel. */
+static unsigned long long g_blend_stats[3];
+ORC_API void orc_blend_stats(unsigned long long out[3])
+{
+    out[0] = g_blend_stats[0]; out[1] = g_blend_stats[1]; out[2] = g_blend_stats[2];
+}
+
 ORC_API void orc_blend(int W, int H, const float* bg, const uint32_t* ranges, const uint32_t* point_list,
                        const float* means_2d, const float* conic, const float* opacity, const float* color,
                        float* img, uint32_t* n_examined, int row0, int row1)
@@ -681,7 +690,8 @@ ORC_API void orc_blend(int W, int H, const float* bg, const uint32_t* ranges, co
     if (row1 < 0) row1 = gy;
     size_t plane = (size_t)W * (size_t)H;
     int    ntile = gx * (row1 - row0);
-#pragma omp parallel for schedule(dynamic, 1)
+    unsigned long long tot_e = 0, tot_a = 0, tot_c = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : tot_e, tot_a, tot_c)
     for (int t = 0; t < ntile; t++) {
         int      bx = t % gx, by = row0 + t / gx;
         uint32_t start = ranges[2 * t], end = ranges[2 * t + 1];
@@ -703,8 +713,10 @@ ORC_API void orc_blend(int W, int H, const float* bg, const uint32_t* ranges, co
                     if (power > 0.0f) continue;
                     float alpha;
                     if (!orc_alpha_passes(op, power, &alpha)) continue;
+                    tot_a++;
                     float test_T = T * (1.0f - alpha);
                     if (test_T < 0.0001f) break; /* done = true; this entry is not blended */
+                    tot_c++;
                     float wgt = T * alpha;
                     C[0] = C[0] + wgt * color[3 * (size_t)id];
                     C[1] = C[1] + wgt * color[3 * (size_t)id + 1];
@@ -714,8 +726,10 @@ ORC_API void orc_blend(int W, int H, const float* bg, const uint32_t* ranges, co
                 size_t pix = (size_t)px + (size_t)W * (size_t)py;
                 for (int c = 0; c < 3; c++) img[pix + c * plane] = bg[c] * T + C[c];
                 if (n_examined) n_examined[pix] = contributor;
+                tot_e += contributor;
             }
     }
+    g_blend_stats[0] = tot_e; g_blend_stats[1] = tot_a; g_blend_stats[2] = tot_c;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -759,7 +773,15 @@ ORC_API long orc_forward(int P, int sh_deg, const float* pos, const float* scale
     orc_inclusive_sum_u32(tiles_touched, offsets, P);
     t1 = orc_now(); if (stage_ms) stage_ms[3] = (t1 - t0) * 1e3; t0 = t1;
     long n = P > 0 ? (long)(int32_t)offsets[P - 1] : 0;
-    if (n <= 0) return 0;
+    /* impl.cpp:109 is about the FRAME's count.  A band of tile rows (row0 / row1: this build's tile-row sharding, no
+     * reference counterpart) whose own count is 0 still belongs to a frame that is rendered, so its tiles get bg. */
+    int whole_frame = (row0 == 0 && row1 == gy);
+    if (n <= 0 && whole_frame) return 0;
+    if (n <= 0) {
+        memset(ranges, 0, (size_t)gx * (size_t)(row1 - row0) * 2 * sizeof(uint32_t));
+        orc_blend(W, H, bg, ranges, vals_sorted, means_2d, conic, opacity, color, img, n_examined, row0, row1);
+        return 0;
+    }
     if ((size_t)n > capacity) return -1;
     orc_copy_with_keys(P, W, H, means_2d, offsets, radii, depth, keys_unsorted, vals_unsorted, row0, row1);
     t1 = orc_now(); if (stage_ms) stage_ms[4] = (t1 - t0) * 1e3; t0 = t1;
@@ -782,6 +804,16 @@ ORC_API void orc_image_to_rgb8(int W, int H, const float* img_chw, uint8_t* rgb)
             size_t idx = (size_t)(H - i - 1) * W + j;
             for (int c = 0; c < 3; c++) rgb[p + c] = (uint8_t)(img_chw[c * plane + idx] * 255);
         }
+}
+
+/* bench.py's CPU legs: torchrun exports OMP_NUM_THREADS=1; the baseline is supposed to use the host's cores */
+ORC_API void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 ORC_API int orc_num_threads(void)

@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
         _lib.orc_exp_monotonicity_violations.argtypes = [C.c_float, C.c_float]
         _lib.orc_forward.restype = C.c_long
         _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_set_num_threads.argtypes = [C.c_int]
+        _lib.orc_set_num_threads.restype = None
     return _lib
 
 
@@ -312,3 +314,15 @@ def forward(pos, scale, rotq, sh, opacity, vp: ViewParams, bg=(0.0, 0.0, 0.0), s
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """Use `n` OpenMP threads from now on (overrides OMP_NUM_THREADS, which torchrun sets to 1)."""
+    lib().orc_set_num_threads(int(n))
+
+
+def blend_stats() -> dict:
+    """Totals of the last blend: E examined (pixel, entry) pairs, E_alpha passed the alpha test, E_contrib blended."""
+    out = (C.c_ulonglong * 3)()
+    lib().orc_blend_stats(out)
+    return {"E": int(out[0]), "E_alpha": int(out[1]), "E_contrib": int(out[2])}

@@ -1,17 +1,30 @@
-# usage: bash scripts/gpu_round.sh <tag> [ncu]   -- GPU tests + bench (+ optional ncu launch list)
+# usage: bash scripts/gpu_round.sh <tag> [ncu] [tune]   -- GPU tests + bench (+ optional ncu launch list, tuning sweep)
 TAG=${1:-x}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_$TAG.log 2>&1; echo pytest rc=$?; tail -12 gpurun_out/pytest_$TAG.log
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo bench rc=$?
+nvidia-smi -L | head -2; nproc
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 --durations=8 > gpurun_out/pytest_$TAG.log 2>&1; echo pytest rc=$?; tail -25 gpurun_out/pytest_$TAG.log
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo bench rc=$?
 python - <<PY
 import json
-d=json.load(open('gpurun_out/bench_$TAG.json'))
-print('ms/frame', round(d['ms_per_step'],3), 'e2e ms', round(d['e2e']['ms_per_step'],3), 'G/s', round(d['value']/1e9,3))
-print({k:v['ms'] for k,v in d['stages'].items()}, d['sort_breakdown'])
-print('roofline', d['roofline']['achieved'], d['roofline']['frac'], 'clocks', d['clocks'])
-print('cpu', d.get('cpu_baseline',{}).get('ms_per_frame'))
+try:
+    d=json.loads(open('gpurun_out/bench_$TAG.json').read().strip().splitlines()[-1])
+    print('ms/frame', round(d['ms_per_step'],4), 'e2e ms', round(d['e2e']['ms_per_step'],4), 'e2e f32 ms', round(d['e2e_float_image']['ms_per_step'],4), 'G/s', round(d['value']/1e9,3))
+    print({k:v['ms'] for k,v in d['stages'].items()}, d['sort_breakdown'])
+    print('roofline', {k: d['roofline'].get(k) for k in ('achieved','frac','peak','E_examined_pairs','E_contrib')})
+    print('roofline_sort', d['roofline_sort']['achieved'], d['roofline_sort']['frac'], 'clocks', d['clocks'])
+    print('cpu', d.get('cpu_baseline',{}).get('ms_per_frame'), 'orbit', {k: d.get('orbit_n1',{}).get(k) for k in ('ms_per_step','frames_per_second','e2e_ms_per_step','consumed_frames_verified','flow_control_timeouts')})
+except Exception as e:
+    print('bench parse failed', e)
 PY
-tail -3 gpurun_out/bench_$TAG.err
-if [ "$2" = "ncu" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.log 2>&1; echo ncu rc=$?
+tail -5 gpurun_out/bench_$TAG.err
+for a in "$@"; do
+if [ "$a" = "ncu" ]; then
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-orbit > gpurun_out/ncu_bench_$TAG.log 2>&1; echo ncu rc=$?
 fi
+if [ "$a" = "tune" ]; then
+export LCGS_TUNING=1
+for v in 2 5 6 7 8 3; do LCGS_SORT_VARIANT=$v timeout 120 python scripts/tune_frame.py C3 2>&1 | tail -1; done
+for o in 4 6; do LCGS_BLEND_OCC=$o timeout 120 python scripts/tune_frame.py C3 2>&1 | tail -1; done
+unset LCGS_TUNING
+fi
+done

@@ -24,6 +24,7 @@ ap.add_argument("--config", default="C3")
 ap.add_argument("--gaussians", type=int, default=400_000)
 ap.add_argument("--views", type=int, default=8)
 ap.add_argument("--capacity", type=int, default=20_000_000)
+ap.add_argument("--skip-views", action="store_true", help="only the tile-row-sharded frame (e.g. the full-size 8K frame)")
 args = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -43,10 +44,13 @@ def render_view(k):
     return r.image().clone()
 
 
+ring = D.PeerFrameRing(dev, W, H, slots=args.views)
+if args.skip_views:
+    out["view_sharded_bit_exact"] = out["view_sharded_peer_bit_exact"] = out["view_sharded_flags_bit_exact"] = None
 torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-frames = D.render_sweep_view_sharded(render_view, args.views)
+frames = D.render_sweep_view_sharded(render_view, 0 if args.skip_views else args.views)
 torch.cuda.synchronize(); dist.barrier(); out["sweep_s"] = time.perf_counter() - t0
-if rank == 0:
+if rank == 0 and not args.skip_views:
     ok = True
     for k in range(args.views):
         want = render_view(k)
@@ -54,7 +58,6 @@ if rank == 0:
     out["view_sharded_bit_exact"] = ok
 
 # ---- the same sweep with the gather fused into the render: peer stores into rank 0's ring ---------------
-ring = D.PeerFrameRing(dev, W, H, slots=args.views)
 
 
 def render_view_into(k, ptr):
@@ -63,15 +66,50 @@ def render_view_into(k, ptr):
 
 
 torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-frames_p = D.render_sweep_view_sharded_peer(render_view_into, args.views, ring)
-out["sweep_peer_s"] = time.perf_counter() - t0
-r.set_target(r.img)
-if rank == 0:
-    ok = True
-    for k in range(args.views):
-        want = render_view(k).cpu().numpy()
-        ok &= bool(np.array_equal(frames_p[k].view(np.uint32), want.view(np.uint32)))
-    out["view_sharded_peer_bit_exact"] = ok
+if not args.skip_views:
+    frames_p = D.render_sweep_view_sharded_peer(render_view_into, args.views, ring)
+    out["sweep_peer_s"] = time.perf_counter() - t0
+    r.set_target(r.img)
+    if rank == 0:
+        ok = True
+        for k in range(args.views):
+            want = render_view(k).cpu().numpy()
+            ok &= bool(np.array_equal(frames_p[k].view(np.uint32), want.view(np.uint32)))
+        out["view_sharded_peer_bit_exact"] = ok
+
+    # ---- stream-ordered hand-over: 2 slots per rank reused through device-side ready / consumed flags, rank 0 checksums
+    # every frame on a consumer stream; 3 * world more views than the ring has slots, no host synchronisation in between
+    ring2 = D.PeerFrameRing(dev, W, H, slots=2 * world)
+    nflag = 5 * world
+    sums = torch.zeros(nflag, dtype=torch.int64, device="cuda")
+    cons = torch.cuda.Stream()
+    for g in range(nflag // world):
+        slot_row, seq = g % 2, g // 2 + 1
+        slot = slot_row * world + rank
+        if g >= 2:
+            ring2.wait_consumed(slot, seq - 1)
+        render_view_into(g * world + rank, ring2.ptr(slot))
+        ring2.signal_ready(slot, seq)
+        if rank == 0:
+            for w in range(world):
+                sl = slot_row * world + w
+                ring2.wait_ready(sl, seq, stream=cons)
+                dev.checksum_u32(ring2.ptr(sl), 3 * W * H, sums[g * world + w:g * world + w + 1], stream=cons)
+                ring2.signal_consumed(sl, seq, stream=cons)
+    torch.cuda.synchronize(); dist.barrier()
+    r.set_target(r.img)
+    t_out = torch.tensor([dev.peer_timeouts()], device="cuda")
+    dist.all_reduce(t_out)
+    if rank == 0:
+        ok = int(t_out.item()) == 0
+        one = torch.zeros(1, dtype=torch.int64, device="cuda")
+        for k in range(nflag):
+            want = render_view(k)
+            dev.checksum_u32(want.data_ptr(), 3 * W * H, one)
+            torch.cuda.synchronize()
+            ok &= bool(int(one.item()) == int(sums[k].item()))
+        out["view_sharded_flags_bit_exact"] = ok
+    ring2.close()
 
 # ---- tile-row sharding: one frame split into bands balanced by instance count ------------------------
 pose = (scenes.CAM_POS, scenes.CAM_TARGET, scenes.world_up(cfg.world))
@@ -99,6 +137,28 @@ def render_band_into(a, b, ptr):
 img_p, _ = D.render_frame_tile_row_sharded_peer(render_band_into, H, ring, slot=0, weights=weights)
 if rank == 0:
     out["tile_row_sharded_peer_bit_exact"] = bool(np.array_equal(img_p.view(np.uint32), full_img.cpu().numpy().view(np.uint32)))
+
+# ---- a band without instances: the last rank owns only the last tile row, which is never binned (Q1); it must still
+# overwrite the slot's stale pixels with the background
+if world >= 2 and args.views >= 2:
+    eb = D.split_tile_rows(gy - 1, world - 1, weights[:gy - 1]) + [(gy - 1, gy)]
+    rb.set_tile_rows(*eb[rank])
+    if rank == 0:  # stale pixels in slot 1 (rank 0 owns the ring: a plain fill of raw device memory)
+        import ctypes
+        dev.check(dev.lib.lcgs_b200_fill_f32(dev.ctx, ctypes.c_void_p(ring.ptr(1)), 3 * W * H, -7.0, None))
+        torch.cuda.synchronize()
+    dist.barrier()
+
+    def render_eb(a, b, ptr):
+        rb.set_target_ptr(ptr)
+        rb.render_async(vp)
+
+    img_e, _ = D.render_frame_tile_row_sharded_peer(render_eb, H, ring, slot=1, bands=eb)
+    n_last = torch.tensor([dev.num_rendered() if rank == world - 1 else 0], device="cuda", dtype=torch.int64)
+    dist.all_reduce(n_last)
+    if rank == 0:
+        out["empty_band_instances"] = int(n_last.item())
+        out["empty_band_bit_exact"] = bool(np.array_equal(img_e.view(np.uint32), full_img.cpu().numpy().view(np.uint32)))
 ring.close()
 if rank == 0:
     out["bands"] = bands
@@ -107,5 +167,9 @@ if rank == 0:
     out["num_rendered"] = n_full
     print(json.dumps(out), flush=True)
     assert out["view_sharded_bit_exact"] and out["tile_row_sharded_bit_exact"] and out["instances_partition_exactly"]
-    assert out["view_sharded_peer_bit_exact"] and out["tile_row_sharded_peer_bit_exact"]
+    assert out["tile_row_sharded_peer_bit_exact"] and out.get("empty_band_bit_exact", True)
+    if not args.skip_views:
+        assert out["view_sharded_peer_bit_exact"] and out["view_sharded_flags_bit_exact"]
+    else:
+        out["view_sharded_bit_exact"] = True
 dist.destroy_process_group()

@@ -11,6 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    config.addinivalue_line("markers", "gpu_multi: needs >= 2 GPUs of one node (gpurun --gpus N -- pytest -m gpu_multi)")
 
 
 def pytest_collection_modifyitems(config, items):

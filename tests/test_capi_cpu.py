@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert declared == set(_capi.EXPORTED_SYMBOLS)  # the Python binding covers the whole header
-    assert _capi.load().lcgs_b200_version() == 100
+    assert _capi.load().lcgs_b200_version() == 200
 
 
 def test_every_entry_point_cites_the_reference():
@@ -76,3 +76,13 @@ def test_library_staleness_is_content_based():
     finally:
         open(b.STAMP, "w").write(stamp)
     assert not b.is_stale()
+
+
+def test_production_library_has_no_tuning_hooks():
+    """Ablation switches and environment-selected kernel geometries exist only in -DLCGS_TUNING builds."""
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", _capi.library_path()], capture_output=True, text=True).stdout
+    assert "lcgs_b200_debug_ablate" not in syms and "tuning_env_int" not in syms
+    data = open(_capi.library_path(), "rb").read()
+    for env in (b"LCGS_SORT_VARIANT", b"LCGS_BLEND_OCC", b"LCGS_REFERENCE_FLOW", b"LCGS_SORT_DEBUG"):
+        assert env not in data, env

@@ -77,7 +77,27 @@ def _worker(rank, world, port, mode, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sc = _scene()
     try:
-        if mode in ("views_peer", "rows_peer"):
+        if mode == "rows_empty_band":
+            # the last rank owns only the last tile row, which is never binned (Q1): its band has 0 instances and must
+            # still overwrite the stale pixels of the slot with the background
+            ring = MemmapRing("/tmp/lcgs_ring_%d.bin" % port, slots=2)
+            if rank == 0:
+                ring.mem[1][:] = -7.0
+            dist.barrier()
+            gy = (H + 15) // 16
+            pose = (scenes.CAM_POS, scenes.CAM_TARGET, scenes.WORLD_UP_COLMAP)
+            bg = (0.25, 0.5, 0.75)
+
+            def band(r0, r1, ptr):
+                vp = orc.view_params(orc.make_camera(*pose, W, H))
+                fr = orc.forward(sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, vp, bg=bg, row0=r0, row1=r1)
+                assert (fr.num_rendered == 0) == (r0 == gy - 1)
+                ring.write(ptr, fr.img, (min(H, 16 * r0), min(H, 16 * r1)))
+
+            img, bands = D.render_frame_tile_row_sharded_peer(band, H, ring, slot=1, bands=[(0, gy - 1), (gy - 1, gy)])
+            if rank == 0:
+                q.put((img, bands))
+        elif mode in ("views_peer", "rows_peer"):
             ring = MemmapRing("/tmp/lcgs_ring_%d.bin" % port, slots=5)
             if mode == "views_peer":
                 out = D.render_sweep_view_sharded_peer(
@@ -152,6 +172,15 @@ def test_peer_drivers_assemble_the_same_frames():
     want = _frame(sc, (scenes.CAM_POS, scenes.CAM_TARGET, scenes.WORLD_UP_COLMAP)).img
     assert bands[0][0] == 0 and bands[-1][1] == (H + 15) // 16
     assert np.array_equal(img.view(np.uint32), want.view(np.uint32))
+
+
+def test_a_band_without_instances_still_writes_the_background():
+    img, bands = _run("rows_empty_band")
+    sc = _scene()
+    vp = orc.view_params(orc.make_camera(scenes.CAM_POS, scenes.CAM_TARGET, scenes.WORLD_UP_COLMAP, W, H))
+    want = orc.forward(sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, vp, bg=(0.25, 0.5, 0.75))
+    assert want.num_rendered > 0 and bands[-1] == ((H + 15) // 16 - 1, (H + 15) // 16)
+    assert np.array_equal(img.view(np.uint32), want.img.view(np.uint32)), "stale pixels left in the empty band"
 
 
 def test_partitioning_helpers():
