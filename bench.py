@@ -336,9 +336,10 @@ class Bench:
         P, W, H, T = r.P, r.W, r.H, r.num_tiles
         V = int((r.depth >= 0.2).sum().item())
         M = int((r.tiles_touched > 0).sum().item())
-        alg = {"preprocess": 56.0 * P + 228.0 * V, "scan": 8.0 * P + 12.0 * M, "depth_sort": 16.0 * M * 3,
+        # preprocess / ranges / blend: SURVEY.md 8d's formulas; scan, depth sort, emission, tile sort: the bytes of the flow that runs
+        alg = {"preprocess": 48.0 * P + 228.0 * V, "scan": 8.0 * P + 12.0 * M, "depth_sort": 16.0 * M * 3,
                "duplicate_keys": 20.0 * M + 12.0 * N, "sort": 24.0 * N * passes, "ranges": 8.0 * N + 16.0 * T,
-               "blend": 52.0 * N + 15.0 * W * H}
+               "blend": 40.0 * N + 12.0 * W * H}
         tab = {k: {"ms": round(v, 4), "alg_GB": round(alg[k] / 1e9, 4), "GBps": round(alg[k] / (v * 1e-3) / 1e9, 1),
                    "frac_of_hbm_peak": round(alg[k] / (v * 1e-3) / 1e9 / peak, 3)} for k, v in stage_ms.items() if v > 0}
         if "blend" in tab:
@@ -389,11 +390,15 @@ class Bench:
             ev_render = [torch.cuda.Event() for _ in range(2)]
             ev_copy = [torch.cuda.Event() for _ in range(2)]
             checksum = 0.0
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for i in range(args.steps):
+            t0 = 0.0
+            for i in range(-warm, args.steps):                  # `warm` untimed iterations of the very same loop first
+                if i == 0:
+                    for e in ev_copy:
+                        e.synchronize()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
                 b = i & 1
-                if i >= 2:
+                if i >= 2 - warm:
                     main_stream.wait_event(ev_copy[b])          # device buffer b has been read out
                 cam = lcgs.make_camera(*pose, W, H)             # host-side camera -> kernel parameters
                 if use_rgb8:
@@ -401,12 +406,12 @@ class Bench:
                 else:
                     r.set_target(dev_bufs[b])
                 r.render_async(lcgs.view_params(cam))
-                r.read_num_rendered_async(host_counts[i:i + 1])
+                r.read_num_rendered_async(host_counts[max(i, 0):max(i, 0) + 1])
                 ev_render[b].record(main_stream)
                 copy_stream.wait_event(ev_render[b])
                 (r.read_image_rgb8 if use_rgb8 else r.read_image)(host_bufs[b], stream=copy_stream)
                 ev_copy[b].record(copy_stream)
-                if i >= 1:
+                if i >= 1 - warm and i != 0:
                     ev_copy[b ^ 1].synchronize()                # frame i-1 is on the host: consume it
                     checksum += float(host_bufs[b ^ 1][12345])
             ev_copy[(args.steps - 1) & 1].synchronize()
@@ -421,7 +426,7 @@ class Bench:
             return dt
         e2e_s = e2e_loop(True)
         e2e_f32_s = e2e_loop(False)
-        self.launches += 2 * KERNELS_PER_FRAME * args.steps
+        self.launches += 2 * KERNELS_PER_FRAME * (args.steps + warm)
 
         # ---- variant: re-upload the whole Gaussian set from pinned host memory every frame ------------
         pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity)]
@@ -517,9 +522,9 @@ class Bench:
                "peak_source": "derived: %d SMs x %d FP32 lanes x 2 x %.0f MHz (median SM clock sampled during the run); "
                               "MEASURED_PEAKS.json has no FP32 figure" % (sm, FP32_LANES_PER_SM, mhz),
                "launch_ms": blend_ms,
-               "hbm": {"alg_bytes_per_launch": 52.0 * N + 15.0 * W * H,
-                       "achieved_GBps": (52.0 * N + 15.0 * W * H) / (blend_ms * 1e-3) / 1e9 if blend_ms else None,
-                       "frac_of_hbm_peak": (52.0 * N + 15.0 * W * H) / (blend_ms * 1e-3) / 1e9 / hbm_peak if blend_ms else None},
+               "hbm": {"alg_bytes_per_launch": 40.0 * N + 12.0 * W * H,
+                       "achieved_GBps": (40.0 * N + 12.0 * W * H) / (blend_ms * 1e-3) / 1e9 if blend_ms else None,
+                       "frac_of_hbm_peak": (40.0 * N + 12.0 * W * H) / (blend_ms * 1e-3) / 1e9 / hbm_peak if blend_ms else None},
                "ncu": self.committed("blend_kernel"), "traffic": self.committed("blend_kernel_dram_bytes_per_launch")}
         if stats and blend_ms:
             E, Ec = stats["E"], stats["E_contrib"]

@@ -109,14 +109,17 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
             float        cov[3];
             ewa_cov2d(a.vp, pv, a.scale_modifier, s0, s1, s2, q.x, q.y, q.z, q.w, cov);
             s = splat_from_cov(pv.ndc_x, pv.ndc_y, cov, a.vp.width, a.vp.height, a.gx, a.gy, a.row0, a.row1);
+            // depth, tile counts and rects are read again within microseconds (scan, emission): normal stores.  radii,
+            // means_2d, conic and colour are outputs nothing in the frame reads back (the blend gathers the packed
+            // records): streaming stores keep them from evicting the former from L2.
             a.depth[i] = pv.z;
-            a.radii[i] = s.radius;
+            __stcs(a.radii + i, s.radius);
             a.tiles[i] = s.tiles;
-            if (a.means_2d) reinterpret_cast<float2*>(a.means_2d)[i] = make_float2(s.px, s.py);
+            if (a.means_2d) __stcs(reinterpret_cast<float2*>(a.means_2d) + i, make_float2(s.px, s.py));
             if (a.conic) {
-                a.conic[3 * i]     = s.conic[0];
-                a.conic[3 * i + 1] = s.conic[1];
-                a.conic[3 * i + 2] = s.conic[2];
+                __stcs(a.conic + 3 * i, s.conic[0]);
+                __stcs(a.conic + 3 * i + 1, s.conic[1]);
+                __stcs(a.conic + 3 * i + 2, s.conic[2]);
             }
             need = s.tiles > 0u;
             if (need && a.rects)
@@ -124,13 +127,13 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
         } else {
             // defined behaviour for near-culled Gaussians (the reference leaves stale data, Q6)
             a.depth[i] = 0.0f;
-            a.radii[i] = 0;
+            __stcs(a.radii + i, 0);
             a.tiles[i] = 0u;
-            if (a.means_2d) reinterpret_cast<float2*>(a.means_2d)[i] = make_float2(0.f, 0.f);
+            if (a.means_2d) __stcs(reinterpret_cast<float2*>(a.means_2d) + i, make_float2(0.f, 0.f));
             if (a.conic) {
-                a.conic[3 * i]     = 0.f;
-                a.conic[3 * i + 1] = 0.f;
-                a.conic[3 * i + 2] = 0.f;
+                __stcs(a.conic + 3 * i, 0.f);
+                __stcs(a.conic + 3 * i + 1, 0.f);
+                __stcs(a.conic + 3 * i + 2, 0.f);
             }
         }
     }
@@ -174,9 +177,9 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_fused_kernel(const __g
             sh_color(a.sh_deg, a.vp.cam_pos, px, py, pz, GlobalSh{ a.sh + (size_t)i * feat * 3 }, rgb);
         }
         if (a.color) {
-            a.color[3 * i]     = rgb[0];
-            a.color[3 * i + 1] = rgb[1];
-            a.color[3 * i + 2] = rgb[2];
+            __stcs(a.color + 3 * i, rgb[0]);
+            __stcs(a.color + 3 * i + 1, rgb[1]);
+            __stcs(a.color + 3 * i + 2, rgb[2]);
         }
         if (!HAS_CONSTS) {
             thr  = alpha_threshold(l2op);

@@ -149,10 +149,15 @@ __global__ void __launch_bounds__(kScanThreads)
     __shared__ ScanPair s_warp[kScanThreads / 32];
     __shared__ uint32_t s_prefix[2];
     const int tid = threadIdx.x;
+    // Persistent CTAs: tiles are taken by ticket (so they start in order and the look-back cannot deadlock), and a
+    // CTA's digit histograms are flushed once at the end instead of once per tile -- with one CTA per tile the
+    // flushes were ~1500 global atomics x 2800 tiles on 2048 addresses.
+    for (;;) {
+    __syncthreads();  // s_tile, s_prefix, s_key / s_idx of the previous tile are no longer read
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    if (tile >= num_tiles) return;
+    if (tile >= num_tiles) break;
     // blocked arrangement: thread t owns items [base + t*8, +8) -> two 16-byte loads per array; the depths
     // are requested up front for every item (4 B each), not one dependent load per touching Gaussian
     const uint32_t e0 = tile * kCompactTile + tid * kCompactItems;
@@ -221,6 +226,7 @@ __global__ void __launch_bounds__(kScanThreads)
                 if (p < digits.num_passes) atomicAdd(&s_hist[(p << digits.radix_bits) + ((key >> digits.shift[p]) & digits.mask[p])], 1u);
         }
     }
+    }  // tile loop
     if (do_hist) {
         __syncthreads();
         for (int k = threadIdx.x; k < nbins; k += kScanThreads) {
@@ -250,7 +256,8 @@ int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const
     uint32_t* ticket = ctx->d_scalars + LCGS_SCALAR_SCAN_TICKET;
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
     auto* st = (unsigned long long*)ctx->scan_ws.ptr;
-    scan_compact_kernel<<<tiles, kScanThreads, 0, s>>>(tiles_touched, depth, (uint32_t)P, tiles, offsets, ckeys, cvals, st,
+    const uint32_t max_blocks = (uint32_t)ctx->num_sms * 6u;  // persistent: 6 x 256 threads per SM
+    scan_compact_kernel<<<tiles < max_blocks ? tiles : max_blocks, kScanThreads, 0, s>>>(tiles_touched, depth, (uint32_t)P, tiles, offsets, ckeys, cvals, st,
                                                        st + tiles, ticket, d_total, d_count, dg, vec_ok);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;

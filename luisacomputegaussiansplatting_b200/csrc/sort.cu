@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         const uint32_t* vsrc = vals_in + (size_t)tile * TILE + q0;
 
         // ---- per digit (thread d): tile histogram, early publish, first look-back window ---------
-        constexpr bool  kCntInRegs = WARPS <= 16 && ITEMS * (int)sizeof(KeyT) < 160;  // otherwise re-read the counters instead of holding them
+        constexpr bool  kCntInRegs = WARPS <= 8 && ITEMS * (int)sizeof(KeyT) < 160;  // otherwise re-read the counters instead of holding them
         uint32_t        tile_count = 0, scan_incl = 0;
         uint32_t        cnt[kCntInRegs ? WARPS : 1];
         uint32_t        st[kLookbackWindow];
@@ -431,9 +431,9 @@ static const SweepVariant<unsigned long long> kSweep64[] = {
     LCGS_SWEEP64(512, 8, 9, 2, true),    // 0: 9-bit digits, MATCH.ANY ranking: long keys (reference flow, 45 bits = 5 passes)
     LCGS_SWEEP64(512, 8, 9, 2, false),   // 1: 9-bit digits, ballot ranking: 15..18 key bits (8K frames)
     LCGS_SWEEP64(256, 20, 7, 2, false),  // 2: 7-bit digits, ballot ranking, 5120-pair tiles: <= 14 key bits (fused flow)
+#ifdef LCGS_TUNING
     LCGS_SWEEP64(256, 12, 7, 4, false),  // 3: same, 3072-pair tiles, 4 CTAs/SM
     LCGS_SWEEP64(512, 8, 7, 2, true),    // 4: 7-bit digits, MATCH.ANY ranking (the earlier default)
-#ifdef LCGS_TUNING
     LCGS_SWEEP64(256, 16, 7, 3, false),  // 5: 4096-pair tiles, 3 CTAs/SM (85 registers)
     LCGS_SWEEP64(256, 24, 7, 2, false),  // 6: 6144-pair tiles
     LCGS_SWEEP64(384, 14, 7, 2, false),  // 7: 5376-pair tiles, 12 warps per CTA
@@ -443,8 +443,10 @@ static const SweepVariant<unsigned long long> kSweep64[] = {
 // 32-bit depth keys of the per-Gaussian sort
 static const SweepVariant<uint32_t> kSweep32[] = {
     LCGS_SWEEP32(512, 16, 9, 1, false),  // 0: one 8192-pair tile per SM, ballot ranking
+#ifdef LCGS_TUNING
     LCGS_SWEEP32(512, 8, 9, 2, false),   // 1
     LCGS_SWEEP32(512, 8, 9, 2, true),    // 2: MATCH.ANY ranking (the earlier default)
+#endif
 };
 constexpr int kMinSweepTile = 2048;
 constexpr size_t kHistSlotBytes = (size_t)kMaxSortPasses * kMaxRadix * sizeof(uint32_t);  // 16 KB, 256-byte multiple

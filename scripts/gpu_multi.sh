@@ -1,12 +1,40 @@
-# usage: bash scripts/gpu_multi.sh N   -- multi-GPU correctness check + bench at N GPUs
-N=${1:-2}
+# usage: bash scripts/gpu_multi.sh N [tests] [c4] [c5]  -- multi-GPU tests and bench lines at N GPUs (gpurun --gpus N)
+N=${1:-2}; shift
 mkdir -p gpurun_out
-nvidia-smi -L | head -$N
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 scripts/multi_gpu_check.py > gpurun_out/multi_check_n$N.json 2> gpurun_out/multi_check_n$N.err; echo check rc=$?; tail -2 gpurun_out/multi_check_n$N.json; tail -3 gpurun_out/multi_check_n$N.err | cut -c1-300
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo bench rc=$?
-tail -3 gpurun_out/bench_n$N.err | cut -c1-300
+nvidia-smi -L | head -$N; nproc
+RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+for a in "$@"; do
+if [ "$a" = "tests" ]; then
+timeout 2400 python -m pytest tests -m gpu_multi -q --timeout 1500 --durations=5 > gpurun_out/pytest_multi_n$N.log 2>&1; echo pytest_multi rc=$?; tail -15 gpurun_out/pytest_multi_n$N.log
+fi
+if [ "$a" = "c4" ]; then
+timeout 900 $RUN --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_c4_n$N.json 2> gpurun_out/bench_c4_n$N.err; echo bench_c4 rc=$?
+tail -3 gpurun_out/bench_c4_n$N.err | cut -c1-400
 python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_n$N.json').read().strip().splitlines()[-1])
-print('N', d['n_gpus'], 'ms/step', round(d['ms_per_step'],3), 'fps', round(d['frames_per_second'],1), 'G/s', round(d['value']/1e9,3), 'e2e G/s', round(d['e2e']['value']/1e9,3))
+try:
+    d=json.loads(open('gpurun_out/bench_c4_n$N.json').read().strip().splitlines()[-1])
+    v=d['view_sharding']
+    print('C4 N', d['n_gpus'], 'ms/step', round(d['ms_per_step'],4), 'fps', round(d['frames_per_second'],1), 'G/s', round(d['value']/1e9,3), 'e2e fps', round(d['e2e']['frames_per_second'],1), 'verified', v['consumed_frames_verified'], 'timeouts', v['flow_control_timeouts'])
+except Exception as e:
+    print('parse failed', e)
 PY
+fi
+if [ "$a" = "c4ref" ]; then
+timeout 900 $RUN --master-port 29513 bench.py --impl reference --gpus $N --steps 5 --warmup 1 > gpurun_out/bench_c4_ref_n$N.json 2> gpurun_out/bench_c4_ref_n$N.err; echo bench_c4_ref rc=$?; cut -c1-300 gpurun_out/bench_c4_ref_n$N.json
+fi
+if [ "$a" = "c5" ]; then
+timeout 1200 $RUN --master-port 29512 bench.py --gpus $N --config C5 --shard rows --steps 10 --warmup 3 > gpurun_out/bench_c5_n$N.json 2> gpurun_out/bench_c5_n$N.err; echo bench_c5 rc=$?
+tail -3 gpurun_out/bench_c5_n$N.err | cut -c1-400
+python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/bench_c5_n$N.json').read().strip().splitlines()[-1])
+    t=d['tile_row_sharding']
+    print('C5 N', d['n_gpus'], 'ms/frame', round(d['ms_per_step'],4), 'e2e ms', round(d['e2e']['ms_per_step'],4), 'imbalance', t['band_imbalance_max_over_mean'], 'uniform', t['uniform_imbalance_max_over_mean'], 'verified', t['assembled_frame_equals_single_gpu_frame'], 'timeouts', t['flow_control_timeouts'])
+    print(' per-rank ms', t['per_rank_ms_per_frame']); print(' stages rank0', t['per_rank_stage_ms'][0])
+except Exception as e:
+    print('parse failed', e)
+PY
+fi
+done

@@ -92,3 +92,53 @@ def test_peer_stores_assemble_views_and_tile_row_bands():
     assert not bad, bad
     assert np.array_equal(img.view(np.uint32), want_img.view(np.uint32)), diff(img, want_img)
     assert float(np.abs(want_img).max()) > 0.0
+
+
+def test_stream_ordered_flags_and_consumer_checksum():
+    """The device-side hand-over (peer_signal / peer_wait / checksum_u32) in one process: a render stream produces 9 frames
+    into a 2-slot ring, a consumer stream checksums each one and releases the slot, nothing synchronises in between;
+    the checksums equal those of frames rendered one by one.  Then a wait on a flag nobody signals gives up after its
+    timeout and is reported."""
+    import torch
+
+    from luisacomputegaussiansplatting_b200 import lcgs, scenes
+
+    sc, cfg = scenes.make_config_scene("C3", P=P)
+    dev = lcgs.Device(0)
+    r = lcgs.Renderer(dev, sc.pos, sc.scale, sc.rotq, sc.sh, sc.opacity, W, H, list_capacity=400_000)
+    n_words, frames, slots = 3 * W * H, 9, 2
+    frame_bytes = ((4 * n_words + 255) // 256) * 256
+    mem = torch.zeros(slots * frame_bytes + 4 * slots * 2, dtype=torch.uint8, device="cuda")
+    base = mem.data_ptr()
+    ready = [base + slots * frame_bytes + 4 * s for s in range(slots)]
+    consumed = [base + slots * frame_bytes + 4 * (slots + s) for s in range(slots)]
+    sums = torch.zeros(frames, dtype=torch.int64, device="cuda")
+    render, consume = torch.cuda.Stream(), torch.cuda.Stream()
+    vps = [lcgs.view_params(lcgs.make_camera(*scenes.orbit_pose(k * 11), W, H)) for k in range(frames)]
+    torch.cuda.synchronize()
+    for k in range(frames):
+        slot, seq = k % slots, k // slots + 1
+        if k >= slots:
+            dev.peer_wait(consumed[slot], seq - 1, stream=render)
+        r.set_target_ptr(base + slot * frame_bytes)
+        r.render_async(vps[k], stream=render)
+        dev.peer_signal(ready[slot], seq, stream=render)
+        dev.peer_wait(ready[slot], seq, stream=consume)
+        dev.checksum_u32(base + slot * frame_bytes, n_words, sums[k:k + 1], stream=consume)
+        dev.peer_signal(consumed[slot], seq, stream=consume)
+    torch.cuda.synchronize()
+    assert dev.peer_timeouts() == 0
+    r.set_target(r.img)
+    one = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for k in range(frames):
+        r.render_async(vps[k])
+        dev.checksum_u32(r.img.data_ptr(), n_words, one)
+        torch.cuda.synchronize()
+        want = int(r.img.view(torch.int32).to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
+        assert int(one.item()) == want, "checksum kernel"
+        assert int(sums[k].item()) == want, "frame %d consumed before it was complete, or overwritten before it was read" % k
+    # a dead peer cannot hang the GPU
+    dev.peer_wait(ready[0], 1000, timeout_ms=50)
+    torch.cuda.synchronize()
+    assert dev.peer_timeouts() == 1
+    dev.close()
