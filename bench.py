@@ -718,19 +718,56 @@ class Bench:
         r, upload_s = self.make_renderer(sc, cfg, args.capacity, tile_rows=bands[rank], rgb8=True)
         steps, warm = args.steps, max(args.warmup, 3)
 
-        # calibration frame on uniform bands -> instances per tile row -> balanced bands
-        n_uniform = r.render(lcgs.make_camera(*pose, W, H))
+        cam = lcgs.make_camera(*pose, W, H)
+
+        def measure():
+            """(instances, device ms per frame) of this rank's current band: 1 warm-up + 3 timed frames into the local image."""
+            n = r.render(cam)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                r.render_async(vp)
+            e1.record()
+            torch.cuda.synchronize()
+            self.launches += 4 * KERNELS_PER_FRAME
+            return n, float(e0.elapsed_time(e1)) / 3.0
+
+        # 1. uniform bands -> instances per tile row (SURVEY.md 8e) and a first set of (instances, rows, ms) samples
+        n_uniform, t_uniform = measure()
         mine = torch.zeros(gy, dtype=torch.float64, device="cuda")
         w_rows = D.row_weights_from_ranges(r.ranges[: 2 * r.num_tiles], r.gx)
         mine[bands[rank][0]:bands[rank][1]] = torch.tensor(w_rows, dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(mine)
         weights = mine.cpu().tolist()
-        uniform_counts = self.gather_counts(n_uniform)
+        uniform_counts, uniform_ms = self.gather_counts(n_uniform), self.gather_counts(t_uniform)
+        samples = [(n, b1 - b0, t) for n, (b0, b1), t in zip(uniform_counts, bands, uniform_ms)]
+        tried = [("uniform rows", bands, uniform_counts, uniform_ms)]
+        # 2. bands balanced by instance count
         bands = D.split_tile_rows(gy, world, weights)
         r.set_tile_rows(*bands[rank])
-        n_band = r.render(lcgs.make_camera(*pose, W, H))
-        band_counts = self.gather_counts(n_band)
+        n_i, t_i = measure()
+        counts_i, ms_i = self.gather_counts(n_i), self.gather_counts(t_i)
+        samples += [(n, b1 - b0, t) for n, (b0, b1), t in zip(counts_i, bands, ms_i)]
+        tried.append(("balanced by instances", bands, counts_i, ms_i))
+        # 3. bands balanced by the measured cost model ms ~ a * instances + b * rows + c (two refinement rounds)
+        cost_model = None
+        if world > 2:
+            for it in range(2):
+                a, b = D.fit_band_cost(samples)
+                cost_model = {"ms_per_million_instances": a * 1e6, "ms_per_tile_row": b, "samples": len(samples)}
+                bands = D.split_tile_rows_by_cost(gy, world, weights, a, b)
+                r.set_tile_rows(*bands[rank])
+                n_c, t_c = measure()
+                counts_c, ms_c = self.gather_counts(n_c), self.gather_counts(t_c)
+                samples += [(n, b1 - b0, t) for n, (b0, b1), t in zip(counts_c, bands, ms_c)]
+                tried.append(("balanced by fitted cost, round %d" % (it + 1), bands, counts_c, ms_c))
+        # the split whose slowest band is fastest
+        best = min(range(len(tried)), key=lambda k: max(tried[k][3]))
+        split_name, bands, band_counts, band_ms = tried[best]
+        r.set_tile_rows(*bands[rank])
+        n_band = r.render(cam)
+        assert n_band == int(band_counts[rank])
 
         SLOTS = 2
         if world > 1:
@@ -851,10 +888,13 @@ class Bench:
                     "note": "camera in from host memory on every rank; every band is blended into rank 0's ring slot, whose uint8 image is "
                             "copied to pinned host memory and read by rank 0's host thread every frame"},
             "tile_row_sharding": {
-                "bands": bands, "instances_per_band": counts, "instances_total": int(sum(counts)),
+                "split": split_name, "bands": bands, "instances_per_band": counts, "instances_total": int(sum(counts)),
                 "band_imbalance_max_over_mean": max(counts) / (sum(counts) / len(counts)) if sum(counts) else None,
-                "uniform_bands_instances": [int(c) for c in uniform_counts],
-                "uniform_imbalance_max_over_mean": max(uniform_counts) / (sum(uniform_counts) / len(uniform_counts)),
+                "band_ms_standalone": [round(float(x), 4) for x in band_ms],
+                "time_imbalance_max_over_mean": max(band_ms) / (sum(band_ms) / len(band_ms)),
+                "cost_model": cost_model,
+                "splits_tried": [{"split": nm, "rows": [b1 - b0 for b0, b1 in bd], "instances": [int(c) for c in cn],
+                                  "ms": [round(float(x), 4) for x in tm], "max_ms": round(max(tm), 4)} for nm, bd, cn, tm in tried],
                 "per_rank_ms_per_frame": [round(float(x), 4) for x in per_rank_ms], "per_rank_stage_ms": all_stage,
                 "assembled_frame_equals_single_gpu_frame": verified, "flow_control_timeouts": int(timeouts),
                 "hbm_floor_ms_per_gpu": "SURVEY.md 8d: 1.13 ms at 8 TB/s for an 8-way split (preprocess replicated)"},

@@ -103,12 +103,56 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v)
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kEmitThreads)
+// Gaussians that cover more than `big_threshold` tiles are not expanded by the warp that owns them (one warp walking a
+// 10 000-tile rect is the whole kernel's tail: on a sparse band of the 8K frame 1 % of the Gaussians hold a third of the
+// instances, and a single warp was found emitting 52 000 instances while the rest of the GPU idled).  The warp only
+// reserves their output range (offsets are chained over the TRUE counts) and appends (entry, piece) work items;
+// emit_big_kernel then expands all pieces of kBigPiece instances, one CTA per piece, perfectly balanced.
+constexpr uint32_t kBigPiece = 2048;
+struct BigEntry {
+    uint32_t dst, cnt, xy0, w, dbits, idx, pad0, pad1;  // first output slot, tile count, x0 | y0<<16, rect width, depth bits, Gaussian
+};
+struct BigLists {
+    BigEntry* entries;
+    uint2*    pieces;    // (entry, piece index)
+    uint32_t* counters;  // [0] entries, [1] pieces
+    uint32_t  entry_capacity, piece_capacity, threshold;
+};
+
+// Tile-bit digit histograms of up to 32 emitted keys (one per lane; every lane of the warp must call).  Consecutive lanes
+// emit consecutive tiles of one Gaussian, so the upper digit is counted once per run of equal digits.
+struct EmitHist {
+    uint32_t hist_addr, hist1_addr, m0, m1;
+    int      sh0, sh1;
+    bool     on, two_digits;
+};
+__device__ __forceinline__ void emit_hist_update(const EmitHist& h, bool emit, uint32_t tile, int lane, unsigned le_mask)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    if (!h.on) return;
+    if (emit) red_shared_add(h.hist_addr + (((tile >> h.sh0) & h.m0) << 2), 1u);
+    if (h.two_digits) {
+        const uint32_t d1      = (tile >> h.sh1) & h.m1;
+        const uint32_t prev    = __shfl_up_sync(FULL, d1, 1);
+        const bool     was     = __shfl_up_sync(FULL, emit ? 1 : 0, 1) != 0;
+        const bool     lead    = emit && (lane == 0 || prev != d1 || !was);
+        const unsigned leaders = __ballot_sync(FULL, lead);
+        const unsigned emits   = __ballot_sync(FULL, emit);
+        if (lead) {
+            // the run ends at the next leader or at the first lane above that does not emit
+            const unsigned stop = (leaders | ~emits) & ~le_mask;
+            const int      end  = stop ? __ffs(stop) - 1 : 32;
+            red_shared_add(h.hist1_addr + (d1 << 2), (uint32_t)(end - lane));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kEmitThreads, 5)
     duplicate_keys_sorted_kernel(const uint32_t* __restrict__ d_m, uint32_t m_capacity, uint32_t gx, uint32_t row0,
                                  const __grid_constant__ SortedPairsU32 sorted, const uint2* __restrict__ rects,
                                  unsigned long long* status, uint32_t* ticket, unsigned long long* __restrict__ keys,
                                  uint32_t* __restrict__ vals, size_t capacity, const __grid_constant__ SortDigits digits,
-                                 bool exact_div)
+                                 bool exact_div, const __grid_constant__ BigLists big)
 {
     // digit histograms of the tile bits of the emitted keys (two passes at most: the tile sort then skips
     // its histogram kernel).  Consecutive lanes emit consecutive tiles of one Gaussian, so the upper digit
@@ -123,9 +167,8 @@ __global__ void __launch_bounds__(kEmitThreads)
     const unsigned FULL = 0xFFFFFFFFu;
     for (int k = tid; k < nbins; k += kEmitThreads) s_hist[k] = 0u;
     const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(s_hist);
-    const int      sh0 = digits.shift[0] - 32, sh1 = digits.shift[1] - 32;
-    const uint32_t m0 = digits.mask[0], m1 = digits.mask[1], hist1_addr = hist_addr + (4u << digits.radix_bits);
-    const bool     two_digits = digits.num_passes > 1;
+    const EmitHist eh{ hist_addr, hist_addr + (4u << digits.radix_bits), digits.mask[0], digits.mask[1],
+                       digits.shift[0] - 32, digits.shift[1] - 32, do_hist, digits.num_passes > 1 };
 
     uint32_t M = *d_m;
     if (M > m_capacity) M = m_capacity;
@@ -194,20 +237,42 @@ __global__ void __launch_bounds__(kEmitThreads)
         __syncthreads();
         const uint32_t wbase = s_base + wpre;  // output offset of this warp's first instance
 
-        // ---- emit: a chunk's instances are one contiguous run of the output; slot p of the run goes to
-        // excl0 + p, loc = start of each Gaussian inside the run ------------------------------------------
+        // ---- emit: a chunk's instances are one contiguous run of the output, minus the ranges of its big Gaussians,
+        // which are handed to emit_big_kernel.  Slot p of the chunk's INLINE run belongs to the lane `l` whose inline
+        // run contains it and goes to that Gaussian's true output offset + (p - start of its inline run). ----------
 #pragma unroll
         for (int c = 0; c < kEmitItems; c++) {
-            const bool     valid = idx[c] != 0xFFFFFFFFu;
-            const uint32_t excl0 = wbase + cbase[c];
-            const uint32_t total = __shfl_sync(FULL, incl[c], 31);
-            const uint32_t loc   = incl[c] - cnt[c];
+            const bool     valid  = idx[c] != 0xFFFFFFFFu;
+            const uint32_t texcl  = wbase + cbase[c] + incl[c] - cnt[c];  // first output slot of this lane's Gaussian
+            const bool     is_big = valid && cnt[c] > big.threshold;
+            if (is_big) {
+                const uint32_t np = (cnt[c] + kBigPiece - 1) / kBigPiece;
+                const uint32_t e  = atomicAdd(big.counters, 1u);
+                const uint32_t pb = atomicAdd(big.counters + 1, np);
+                if (e < big.entry_capacity) {
+                    big.entries[e] = BigEntry{ texcl, cnt[c], xy0[c], w[c], dbits[c], idx[c], 0u, 0u };
+                    for (uint32_t k = 0; k < np; k++)
+                        if (pb + k < big.piece_capacity) big.pieces[pb + k] = make_uint2(e, k);
+                }
+            }
+            const bool     any_big = __any_sync(FULL, is_big);
+            const uint32_t icnt    = is_big ? 0u : cnt[c];
+            uint32_t       iincl   = incl[c];
+            if (any_big) {  // inline counts need their own scan
+                iincl = icnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(FULL, iincl, d);
+                    if (lane >= d) iincl += y;
+                }
+            }
+            const uint32_t total = __shfl_sync(FULL, iincl, 31);
+            const uint32_t loc   = iincl - icnt;
             // q = j / w as a multiply-high (exact while j * w < 2^32, checked on the host for the grid)
             const uint32_t magic = (uint32_t)(0x100000000ull / w[c]) + 1u;
-            // Every compacted Gaussian touches a tile, so owners are consecutive lanes and an output slot
-            // finds its owner by counting the Gaussian starts at or before it: one ballot, one
-            // OR-reduction, two popc.
-            const bool dense = exact_div && __all_sync(FULL, !valid || cnt[c] > 0u);
+            // Every compacted Gaussian touches a tile, so (without big ones) owners are consecutive lanes and an output
+            // slot finds its owner by counting the Gaussian starts at or before it: one ballot, one OR-reduction, two popc.
+            const bool dense = exact_div && !any_big && __all_sync(FULL, !valid || cnt[c] > 0u);
             for (uint32_t p0 = 0; p0 < total; p0 += 32) {
                 const uint32_t p = p0 + lane;
                 int            l;
@@ -226,6 +291,7 @@ __global__ void __launch_bounds__(kEmitThreads)
                     }
                 }
                 const uint32_t o_loc   = __shfl_sync(FULL, loc, l);
+                const uint32_t o_texcl = __shfl_sync(FULL, texcl, l);
                 const uint32_t o_xy0   = __shfl_sync(FULL, xy0[c], l);
                 const uint32_t o_w     = __shfl_sync(FULL, w[c], l);
                 const uint32_t o_magic = __shfl_sync(FULL, magic, l);
@@ -237,30 +303,60 @@ __global__ void __launch_bounds__(kEmitThreads)
                 const uint32_t ry   = exact_div ? (o_w == 1u ? j : __umulhi(j, o_magic)) : j / o_w;  // magic wraps for w == 1
                 const uint32_t rx   = j - ry * o_w;
                 const uint32_t tile = ((o_xy0 & 0xFFFFu) + rx) + ((o_xy0 >> 16) + ry - row0) * gx;
-                const size_t   dst  = (size_t)excl0 + p;
+                const size_t   dst  = (size_t)o_texcl + j;
                 const bool     emit = p < total && dst < capacity;
                 if (emit) {
                     keys[dst] = ((unsigned long long)tile << 32) | (unsigned long long)o_dbits;
                     vals[dst] = o_idx;
                 }
-                if (do_hist) {
-                    if (emit) red_shared_add(hist_addr + (((tile >> sh0) & m0) << 2), 1u);
-                    if (two_digits) {
-                        // consecutive lanes emit consecutive tiles: runs of equal upper digits are counted by
-                        // their first lane (MATCH.ANY is slow)
-                        const uint32_t d1      = (tile >> sh1) & m1;
-                        const uint32_t prev    = __shfl_up_sync(FULL, d1, 1);
-                        const bool     lead    = emit && (lane == 0 || prev != d1);
-                        const unsigned leaders = __ballot_sync(FULL, lead);
-                        const int      n_emit  = __popc(__ballot_sync(FULL, emit));
-                        if (lead) {
-                            const unsigned above = leaders & ~le_mask;
-                            const int      end   = above ? __ffs(above) - 1 : n_emit;
-                            red_shared_add(hist1_addr + (d1 << 2), (uint32_t)(end - lane));
-                        }
-                    }
-                }
+                emit_hist_update(eh, emit, tile, lane, le_mask);
             }
+        }
+    }
+    if (do_hist) {
+        __syncthreads();
+        for (int k = tid; k < nbins; k += kEmitThreads) {
+            const uint32_t c = s_hist[k];
+            if (c) atomicAdd(digits.hist + k, c);
+        }
+    }
+}
+
+// One CTA per (entry, piece): kBigPiece consecutive instances of one big Gaussian, coalesced.
+__global__ void __launch_bounds__(kEmitThreads)
+    emit_big_kernel(uint32_t gx, uint32_t row0, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, size_t capacity,
+                    const __grid_constant__ SortDigits digits, bool exact_div, const __grid_constant__ BigLists big)
+{
+    __shared__ uint32_t s_hist[2 * 512];
+    const bool     do_hist = digits.hist != nullptr;
+    const int      nbins   = do_hist ? (digits.num_passes << digits.radix_bits) : 0;
+    const int      tid = threadIdx.x, lane = tid & 31;
+    const unsigned le_mask = (2u << lane) - 1u;
+    for (int k = tid; k < nbins; k += kEmitThreads) s_hist[k] = 0u;
+    const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(s_hist);
+    const EmitHist eh{ hist_addr, hist_addr + (4u << digits.radix_bits), digits.mask[0], digits.mask[1],
+                       digits.shift[0] - 32, digits.shift[1] - 32, do_hist, digits.num_passes > 1 };
+    __syncthreads();
+    uint32_t np = big.counters[1];
+    if (np > big.piece_capacity) np = big.piece_capacity;
+    for (uint32_t q = blockIdx.x; q < np; q += gridDim.x) {
+        const uint2 pc = __ldg(big.pieces + q);
+        if (pc.x >= big.entry_capacity) continue;
+        const BigEntry e     = big.entries[pc.x];
+        const uint32_t magic = (uint32_t)(0x100000000ull / e.w) + 1u;
+        const uint32_t j0 = pc.y * kBigPiece, j1 = min(e.cnt, j0 + kBigPiece);
+        for (uint32_t jb = j0; jb < j1; jb += kEmitThreads) {  // uniform trip count: the histogram helper is warp-synchronous
+            const uint32_t j    = jb + tid;
+            const uint32_t ry   = exact_div ? (e.w == 1u ? j : __umulhi(j, magic)) : j / e.w;
+            const uint32_t rx   = j - ry * e.w;
+            const uint32_t tile = ((e.xy0 & 0xFFFFu) + rx) + ((e.xy0 >> 16) + ry - row0) * gx;
+            const size_t   dst  = (size_t)e.dst + j;
+            const bool     emit = j < j1 && dst < capacity;
+            if (emit) {
+                keys[dst] = ((unsigned long long)tile << 32) | (unsigned long long)e.dbits;
+                vals[dst] = e.idx;
+            }
+            emit_hist_update(eh, emit, tile, lane, le_mask);
         }
     }
     if (do_hist) {
@@ -339,6 +435,24 @@ int launch_duplicate_keys(lcgs_b200_ctx* ctx, int P, int W, int H, const float* 
     return LCGS_B200_OK;
 }
 
+static size_t emit_ws_layout(int P, size_t capacity, uint32_t* threshold, uint32_t* entry_capacity, uint32_t* piece_capacity,
+                             size_t* entries_bytes)
+{
+    *threshold         = (uint32_t)LCGS_TUNE_INT("LCGS_EMIT_BIG", 128);
+    const size_t by_p  = (size_t)(P > 0 ? P : 1), by_cap = capacity / ((size_t)*threshold + 1) + 1;
+    *entry_capacity    = (uint32_t)(by_p < by_cap ? by_p : by_cap);
+    *piece_capacity    = (uint32_t)(capacity / kBigPiece + *entry_capacity + 1);
+    *entries_bytes     = (size_t)*entry_capacity * sizeof(BigEntry);
+    return *entries_bytes + (size_t)*piece_capacity * sizeof(uint2);
+}
+
+size_t emit_ws_bytes(int P, size_t capacity)
+{
+    uint32_t t, e, p;
+    size_t   b;
+    return emit_ws_layout(P, capacity, &t, &e, &p, &b);
+}
+
 int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, int H, int num_rows,
                                  const SortedPairsU32& sorted, const uint2* rects, uint64_t* keys, uint32_t* vals,
                                  size_t capacity, int row0, const SortDigits* digits, cudaStream_t s)
@@ -362,14 +476,26 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
     if (rc) return rc;
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->scan_ws.ptr, 0, (size_t)tiles * sizeof(unsigned long long), s));
     uint32_t* ticket = ctx->d_scalars + LCGS_SCALAR_DUP_TICKET;
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
+    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, 3 * sizeof(uint32_t), s));  // ticket + the two big-list counters
+    // side lists of the big Gaussians: each holds more than `threshold` instances, so a frame within its list capacity
+    // has at most capacity / (threshold + 1) of them (a frame that overflows is reported as such; entries beyond are dropped)
+    BigLists big;
+    size_t   entries_bytes;
+    const size_t emit_bytes = emit_ws_layout(P, capacity, &big.threshold, &big.entry_capacity, &big.piece_capacity, &entries_bytes);
+    if ((rc = ws_reserve(ctx, ctx->emit_ws, emit_bytes))) return rc;
+    big.entries  = (BigEntry*)ctx->emit_ws.ptr;
+    big.pieces   = (uint2*)((char*)ctx->emit_ws.ptr + entries_bytes);
+    big.counters = ticket + 1;
     // persistent CTAs; tiles are handed out by ticket, so CTAs that are not resident yet hold nothing back
     const uint32_t max_blocks = (uint32_t)ctx->num_sms * 6u;
     const uint32_t blocks     = tiles < max_blocks ? tiles : max_blocks;
     duplicate_keys_sorted_kernel<<<blocks, kEmitThreads, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, sorted, rects,
                                                                 (unsigned long long*)ctx->scan_ws.ptr, ticket,
                                                                 reinterpret_cast<unsigned long long*>(keys), vals, capacity,
-                                                                dg, exact_div);
+                                                                dg, exact_div, big);
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    emit_big_kernel<<<max_blocks, kEmitThreads, 0, s>>>(gx, (uint32_t)row0, reinterpret_cast<unsigned long long*>(keys), vals, capacity,
+                                                        dg, exact_div, big);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }

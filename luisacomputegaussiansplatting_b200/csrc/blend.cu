@@ -264,23 +264,35 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
         if (__syncthreads_and(T < 0.0f)) break;
     }
 
+    T = fabsf(T);
+    const float v0 = __fmaf_rn(bg0, T, C0), v1 = __fmaf_rn(bg1, T, C1), v2 = __fmaf_rn(bg2, T, C2);
     if (inside) {
         const size_t plane = (size_t)W * (size_t)H;
         const size_t pix   = (size_t)px + (size_t)W * (size_t)py;
-        T                    = fabsf(T);
-        img[pix]             = __fmaf_rn(bg0, T, C0);
-        img[pix + plane]     = __fmaf_rn(bg1, T, C1);
-        const float v0 = __fmaf_rn(bg0, T, C0), v1 = __fmaf_rn(bg1, T, C1), v2 = __fmaf_rn(bg2, T, C2);
         img[pix]             = v0;
         img[pix + plane]     = v1;
         img[pix + 2 * plane] = v2;
-        if (rgb8) {
-            // the app's post-process fused into the epilogue (app/main.cpp:322-337): HWC, vertical flip,
-            // uint8(v * 255) with truncation (cvt.rzi saturates at 0; 255 caps what C leaves undefined)
-            uint8_t* o = rgb8 + ((size_t)(H - 1 - py) * (size_t)W + (size_t)px) * 3;
-            o[0] = (uint8_t)min(__float2uint_rz(v0 * 255.0f), 255u);
-            o[1] = (uint8_t)min(__float2uint_rz(v1 * 255.0f), 255u);
-            o[2] = (uint8_t)min(__float2uint_rz(v2 * 255.0f), 255u);
+    }
+    if (rgb8) {
+        // The app's post-process fused into the epilogue (app/main.cpp:322-337): HWC, vertical flip, uint8(v * 255) with
+        // truncation (cvt.rzi saturates at 0; 255 caps what C leaves undefined).  The tile's 16 x 48 bytes are staged in
+        // shared memory (the record buffers are free now) and leave as runs of 32 consecutive bytes per warp instruction:
+        // per-pixel byte stores were 96 partial-sector writes per tile, which is what the NVLink ingress of the rank that
+        // owns a multi-GPU frame ring chokes on when 7 peers blend into it.
+        unsigned char* const s_u8 = reinterpret_cast<unsigned char*>(&s_rec[0][0][0]);
+        __syncthreads();  // every warp has left the round loop: nobody reads the record buffers any more
+        if (inside) {
+            const int o = ((py - tile_y0) * 16 + (px - tile_x0)) * 3;
+            s_u8[o]     = (unsigned char)min(__float2uint_rz(v0 * 255.0f), 255u);
+            s_u8[o + 1] = (unsigned char)min(__float2uint_rz(v1 * 255.0f), 255u);
+            s_u8[o + 2] = (unsigned char)min(__float2uint_rz(v2 * 255.0f), 255u);
+        }
+        __syncthreads();
+        const int cols = min(16, W - tile_x0) * 3;  // valid bytes per tile row
+#pragma unroll
+        for (int k = tid; k < 16 * 48; k += kBlendThreads) {
+            const int row = k / 48, col = k - row * 48, y = tile_y0 + row;
+            if (y < H && col < cols) rgb8[((size_t)(H - 1 - y) * (size_t)W + (size_t)tile_x0) * 3 + col] = s_u8[k];
         }
     }
 }

@@ -191,6 +191,7 @@ static int reserve_all(lcgs_b200_ctx* ctx, int P, size_t max_instances)
         // look-back status: 2 chains x P/2048 tiles (scan + compaction), P/256 tiles (instance emission)
         if ((rc = ws_reserve(ctx, ctx->scan_ws, (((size_t)P + 255) / 256) * sizeof(unsigned long long)))) return rc;
         if ((rc = ws_reserve(ctx, ctx->order_ws, (size_t)P * 24))) return rc;
+        if ((rc = ws_reserve(ctx, ctx->emit_ws, emit_ws_bytes(P, max_instances)))) return rc;
     }
     const size_t sort_items = max_instances > (size_t)(P > 0 ? P : 0) ? max_instances : (size_t)(P > 0 ? P : 0);
     if (sort_items > 0)
@@ -259,6 +260,7 @@ int lcgs_b200_ctx_destroy(lcgs_b200_ctx* ctx)
     if (ctx->record_ws.ptr) cudaFree(ctx->record_ws.ptr);
     if (ctx->order_ws.ptr) cudaFree(ctx->order_ws.ptr);
     if (ctx->tile_order_ws.ptr) cudaFree(ctx->tile_order_ws.ptr);
+    if (ctx->emit_ws.ptr) cudaFree(ctx->emit_ws.ptr);
     sort_free_plans(ctx);
     for (int i = 0; i < 16; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

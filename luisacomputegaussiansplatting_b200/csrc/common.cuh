@@ -53,6 +53,7 @@ struct lcgs_b200_ctx {
     lcgs_b200::Workspace record_ws;   // packed per-Gaussian blend records
     lcgs_b200::Workspace order_ws;    // fused path: packed rects + compacted/sorted (depth, index) pairs + offsets
     lcgs_b200::Workspace tile_order_ws;  // blend: tile ids, longest list first
+    lcgs_b200::Workspace emit_ws;        // emission: entries + pieces of the Gaussians expanded by emit_big_kernel
     // per-stage timing
     int          profiling  = 0;
     cudaEvent_t  ev[16];
@@ -70,11 +71,11 @@ struct lcgs_b200_ctx {
 #define LCGS_SCALAR_NUM_TOUCHING 1   /* Gaussians with tiles_touched > 0 (fused path) */
 #define LCGS_SCALAR_SCAN_TICKET  2
 #define LCGS_SCALAR_SORT_TICKET  3   /* .. 3 + kMaxSortPasses - 1 */
-#define LCGS_SCALAR_DUP_TICKET   12
+#define LCGS_SCALAR_DUP_TICKET   16  /* + 17, 18: entry / piece counters of the emission's big-Gaussian lists */
 #define LCGS_SCALAR_OVERFLOW     13  /* 1 iff the last frame's num_rendered exceeded its list_capacity (device-side test) */
 #define LCGS_SCALAR_CAPACITY     14  /* that frame's list_capacity (clamped to 2^32-1), written in-stream; = OVERFLOW + 1 */
 #define LCGS_SCALAR_PEER_TIMEOUTS 15  /* sticky: peer waits that gave up (lcgs_b200_peer_error) */
-#define LCGS_NUM_SCALARS         16
+#define LCGS_NUM_SCALARS         24
 
 #define LCGS_CUDA_CHECK(ctx, expr)                                                                   \
     do {                                                                                             \
@@ -153,6 +154,7 @@ int launch_duplicate_keys(lcgs_b200_ctx* ctx, int P, int W, int H, const float* 
                           const int32_t* radii, const float* depth, uint64_t* keys, uint32_t* vals, size_t capacity,
                           int row0, int row1, cudaStream_t s);
 size_t sort_temp_bytes(size_t n);
+size_t emit_ws_bytes(int P, size_t capacity);
 int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
                 uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
                 cudaStream_t s);

@@ -66,6 +66,28 @@ def row_weights_from_ranges(ranges: torch.Tensor, gx: int) -> List[float]:
     return per_tile[: rows * gx].view(rows, gx).sum(dim=1).to(torch.float64).cpu().tolist()
 
 
+def fit_band_cost(samples: Sequence[Tuple[float, float, float]]) -> Tuple[float, float]:
+    """Least-squares fit of measured band times, ms ~ a * instances + b * tile_rows + c, over `samples` =
+    (instances, tile_rows, ms) of several bands (ideally from two different splits, so that instances and rows
+    vary independently).  Returns (a, b) clipped to >= 0: the cost of one more instance and of one more tile row.
+    Balancing by instance count alone leaves wide, sparse bands up to 1.8x slower than narrow dense ones
+    (per-tile and per-pixel work in the blend, fewer and bigger Gaussians in the emission)."""
+    import numpy as np
+
+    A = np.array([[n, r, 1.0] for n, r, _ in samples], np.float64)
+    y = np.array([t for _, _, t in samples], np.float64)
+    if len(samples) < 3 or np.linalg.matrix_rank(A) < 3:
+        return 1.0, 0.0
+    (a, b, _c), *_ = np.linalg.lstsq(A, y, rcond=None)
+    a, b = max(float(a), 0.0), max(float(b), 0.0)
+    return (a, b) if (a > 0.0 or b > 0.0) else (1.0, 0.0)
+
+
+def split_tile_rows_by_cost(num_rows: int, world: int, weights: Sequence[float], a: float, b: float) -> List[Tuple[int, int]]:
+    """Bands balanced by the fitted cost a * instances_in_row + b per tile row (see fit_band_cost)."""
+    return split_tile_rows(num_rows, world, [a * float(w) + b for w in weights])
+
+
 # --------------------------------------------------------------------------------------------------
 # collectives (the only exchange steps of the path)
 # --------------------------------------------------------------------------------------------------

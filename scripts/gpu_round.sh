@@ -23,8 +23,23 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-fil
 fi
 if [ "$a" = "tune" ]; then
 export LCGS_TUNING=1
-for v in 2 5 6 7 8 3; do LCGS_SORT_VARIANT=$v timeout 120 python scripts/tune_frame.py C3 2>&1 | tail -1; done
-for o in 4 6; do LCGS_BLEND_OCC=$o timeout 120 python scripts/tune_frame.py C3 2>&1 | tail -1; done
+for v in 2 3 4 5 6 7 8; do LCGS_SORT_VARIANT=$v timeout 120 python scripts/tune_frame.py C3 2>&1 | tail -1; done
+for b in 32 64 256 1000000; do LCGS_EMIT_BIG=$b timeout 120 python scripts/tune_frame.py C3 2>&1 | tail -1; done
 unset LCGS_TUNING
+fi
+if [ "$a" = "c5" ]; then
+timeout 600 python bench.py --config C5 --shard rows --steps 10 --warmup 3 > gpurun_out/bench_c5_n1_$TAG.json 2> gpurun_out/bench_c5_n1_$TAG.err; echo bench_c5 rc=$?; tail -2 gpurun_out/bench_c5_n1_$TAG.err
+python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/bench_c5_n1_$TAG.json').read().strip().splitlines()[-1])
+    print('C5 N=1 ms/frame', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['ms_per_step'],4), d['tile_row_sharding']['per_rank_stage_ms'])
+except Exception as e:
+    print('parse failed', e)
+PY
+fi
+if [ "$a" = "ncufull" ]; then
+ncu --set full --clock-control none --import-source on -k "regex:blend_kernel|onesweep_pass|preprocess_fused|duplicate_keys_sorted|scan_compact|emit_big|tile_ranges|tile_order" -s 36 -c 13 -f -o gpurun_out/full_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-orbit > gpurun_out/ncu_full_$TAG.log 2>&1; echo ncufull rc=$?
+python scripts/ncu_export.py gpurun_out/full_$TAG.ncu-rep gpurun_out/full_$TAG.csv | tail -1
 fi
 done

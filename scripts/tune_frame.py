@@ -28,5 +28,10 @@ for it in range(13):
         st = dev.stage_times()
         acc = st if acc is None else {k: acc[k] + st[k] for k in st}
 avg = {k: round(v / 10, 4) for k, v in acc.items()}
+import torch
+n = dev.num_rendered()
+pos = torch.arange(n, device="cuda", dtype=torch.int64) % 1000003
+sig = (int((r.keys[:n] * (pos + 1)).sum().item()) & 0xFFFFFFFFFFFF, int((r.vals[:n].to(torch.int64) * (pos + 7)).sum().item()) & 0xFFFFFFFFFFFF,
+       int(r.img.view(torch.int32).to(torch.int64).sum().item()) & 0xFFFFFFFFFFFF, int(r.ranges.to(torch.int64).sum().item()))
 env = {k: v for k, v in os.environ.items() if k.startswith("LCGS_")}
-print("%s total %.4f %s" % (env, sum(avg.values()), avg), flush=True)
+print("%s total %.4f %s sig %s" % (env, sum(avg.values()), avg, "%x.%x.%x.%x" % sig), flush=True)
