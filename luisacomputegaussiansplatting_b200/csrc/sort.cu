@@ -56,11 +56,6 @@ __device__ __forceinline__ void cp_async_u32(uint32_t smem_addr, const uint32_t*
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
-template <typename T>
-__device__ __forceinline__ void cp_async_u64(uint32_t smem_addr, const T* gptr)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ size_t resolve_n(size_t n_host, const uint32_t* d_n, size_t capacity)
@@ -186,10 +181,7 @@ __device__ __forceinline__ unsigned digit_peers(uint32_t d)
 
 // HI: the digit lies entirely in the upper 32 bits of a 64-bit key (every pass of the tile sort), so it is a
 // shift and a mask of one register; otherwise a funnel shift over both words.
-// LEAN (64-bit keys, HI only): the thread keeps only the upper key words (the digit source) and 16-bit ranks in
-// registers; the full keys travel global -> shared memory by LDGSTS at scatter time, like the values.  That is
-// 20 + 10 registers for a 20-item tile instead of 40 + 20, which buys a third CTA per SM for a latency-bound kernel.
-template <typename KeyT, int THREADS, int ITEMS, int RBITS, int MIN_BLOCKS, bool USE_MATCH, bool HI, bool LEAN = false>
+template <typename KeyT, int THREADS, int ITEMS, int RBITS, int MIN_BLOCKS, bool USE_MATCH, bool HI>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                          const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, size_t n_host,
@@ -203,8 +195,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit");
     static_assert((WARPS * RADIX) % THREADS == 0, "counter zeroing");
     static_assert(RADIX % 32 == 0 && THREADS * ITEMS <= 65536, "digit warps are whole warps; tile slots fit 16 bits");
-    static_assert(!LEAN || (HI && sizeof(KeyT) == 8 && ITEMS % 2 == 0), "LEAN: 64-bit keys with the digit in the upper word");
-    using RegKeyT = std::conditional_t<LEAN, uint32_t, KeyT>;  // what a thread holds per item between load and scatter
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyT* const               s_keys   = reinterpret_cast<KeyT*>(smem_raw);
@@ -221,7 +211,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const uint32_t q0        = warp * (ITEMS * 32) + lane;  // warp-striped: item j sits at q0 + 32*j
     const bool     is_digit  = tid < RADIX;
     const uint32_t  s_vals_addr = (uint32_t)__cvta_generic_to_shared(s_vals);
-    const uint32_t  s_keys_addr = (uint32_t)__cvta_generic_to_shared(s_keys);
     uint32_t* const my_hist  = s_wh + warp * RADIX;
     const uint32_t  my_hist_addr = (uint32_t)__cvta_generic_to_shared(my_hist);
     // every key has digit 0 in this pass (the top bits of the depth keys): the pass is the identity
@@ -229,11 +218,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     if ((flags & kSweepSkipIfTrivial) && __ldg(hist) == (uint32_t)n) return;
 
     auto digit_of = [&](KeyT k) -> uint32_t { return HI ? key_digit_hi(k, shift, mask) : key_digit(k, shift, mask); };
-    // digit of the register copy of a key (LEAN: the upper word alone)
-    auto digit_of_reg = [&](RegKeyT k) -> uint32_t {
-        if constexpr (LEAN) return (k >> (shift - 32)) & mask;
-        else return digit_of(k);
-    };
     auto tile_valid = [&](uint32_t t) -> uint32_t {
         const size_t base = (size_t)t * TILE;
         return (uint32_t)((n - base) < (size_t)TILE ? (n - base) : (size_t)TILE);
@@ -252,16 +236,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     __syncthreads();
     uint32_t tile = s_ticket[0];
 
-    RegKeyT key[ITEMS];
+    KeyT key[ITEMS];
     auto load_keys = [&](uint32_t t) {
         if (t >= num_tiles) return;
         const KeyT* src = keys_in + (size_t)t * TILE + q0;
         const uint32_t            nv  = tile_valid(t);
-        if constexpr (LEAN) {
-            const uint32_t* hsrc = reinterpret_cast<const uint32_t*>(src) + 1;  // little endian: the upper words
-#pragma unroll
-            for (int j = 0; j < ITEMS; j++) key[j] = (nv == (uint32_t)TILE || q0 + 32 * j < nv) ? __ldg(hsrc + 64 * j) : ~0u;
-        } else if (nv == (uint32_t)TILE) {
+        if (nv == (uint32_t)TILE) {
 #pragma unroll
             for (int j = 0; j < ITEMS; j++) key[j] = __ldg(src + 32 * j);
         } else {
@@ -281,22 +261,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         // match_any; the lowest of them adds the group to the warp's counter with ONE shared-memory atomic
         // and hands the old value to its peers by shuffle.  No register dependency between the items (the
         // same-address atomics of a warp execute in program order), so the 8 chains overlap.
-        uint32_t rd[LEAN ? ITEMS / 2 : ITEMS];  // (digit << 16) | rank inside (warp, digit); LEAN: two 16-bit ranks per word
+        uint32_t rd[ITEMS];  // (digit << 16) | rank inside (warp, digit); after the scatter: slot in the tile
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             const bool     valid  = full || q0 + 32 * j < nvalid;
-            const uint32_t d      = valid ? digit_of_reg(key[j]) : (uint32_t)RADIX;
+            const uint32_t d      = valid ? digit_of(key[j]) : (uint32_t)RADIX;
             const unsigned peers  = digit_peers<full ? RBITS : RBITS + 1, USE_MATCH>(d);
             const unsigned lower  = peers & lt_mask;
             uint32_t       before = 0;
             if (valid && lower == 0u) before = atom_shared_add(my_hist_addr + d * 4u, (uint32_t)__popc(peers));
             before = __shfl_sync(0xFFFFFFFFu, before, __ffs(peers) - 1);
-            if constexpr (LEAN) {
-                const uint32_t rank = before + __popc(lower);  // < 32 * ITEMS
-                rd[j >> 1]          = (j & 1) ? (rd[j >> 1] | (rank << 16)) : rank;
-            } else {
-                rd[j] = (d << 16) | (before + __popc(lower));
-            }
+            rd[j]  = (d << 16) | (before + __popc(lower));
         }
         __syncthreads();
         const uint32_t next_tile = s_ticket[1];
@@ -306,7 +281,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         // and the copies are waited for behind the look-back.  Holding ITEMS values in registers from here
         // to the scatter made the 256 x 20 geometry spill at its 128-register budget.
         const uint32_t* vsrc = vals_in + (size_t)tile * TILE + q0;
-        const KeyT*     ksrc = keys_in + (size_t)tile * TILE + q0;  // LEAN: the keys are fetched again, straight into their slots
 
         // ---- per digit (thread d): tile histogram, early publish, first look-back window ---------
         constexpr bool  kCntInRegs = WARPS <= 8 && ITEMS * (int)sizeof(KeyT) < 160;  // otherwise re-read the counters instead of holding them
@@ -357,15 +331,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             if (full || q0 + 32 * j < nvalid) {
-                if constexpr (LEAN) {
-                    const uint32_t slot = ((rd[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu) + my_hist[digit_of_reg(key[j])];
-                    cp_async_u64(s_keys_addr + slot * 8u, ksrc + 32 * j);
-                    cp_async_u32(s_vals_addr + slot * 4u, vsrc + 32 * j);
-                } else {
-                    const uint32_t slot = (rd[j] & 0xFFFFu) + my_hist[rd[j] >> 16];
-                    s_keys[slot] = key[j];
-                    cp_async_u32(s_vals_addr + slot * 4u, vsrc + 32 * j);
-                }
+                const uint32_t slot = (rd[j] & 0xFFFFu) + my_hist[rd[j] >> 16];
+                s_keys[slot] = key[j];
+                cp_async_u32(s_vals_addr + slot * 4u, vsrc + 32 * j);
             }
         }
         // this warp's counters are free again: clear them for its next tile (only the warp itself touches
@@ -453,9 +421,6 @@ struct SweepVariant {
 #define LCGS_SWEEP64(T, I, R, B, M)                                                                                         \
     { { onesweep_pass_kernel<unsigned long long, T, I, R, B, M, false>, onesweep_pass_kernel<unsigned long long, T, I, R, B, M, true> }, \
       T, T * I, R, B, sweep_smem_bytes<unsigned long long, T, I, R>(), #T "x" #I " r" #R " " #B "/SM" }
-#define LCGS_SWEEP64_LEAN(T, I, R, B)                                                                                        \
-    { { onesweep_pass_kernel<unsigned long long, T, I, R, B, false, false>, onesweep_pass_kernel<unsigned long long, T, I, R, B, false, true, true> }, \
-      T, T * I, R, B, sweep_smem_bytes<unsigned long long, T, I, R>(), #T "x" #I " r" #R " " #B "/SM lean" }
 #define LCGS_SWEEP32(T, I, R, B, M)                                                                    \
     { { onesweep_pass_kernel<uint32_t, T, I, R, B, M, false>, onesweep_pass_kernel<uint32_t, T, I, R, B, M, false> }, \
       T, T * I, R, B, sweep_smem_bytes<uint32_t, T, I, R>(), #T "x" #I " r" #R " " #B "/SM" }
@@ -466,15 +431,13 @@ static const SweepVariant<unsigned long long> kSweep64[] = {
     LCGS_SWEEP64(512, 8, 9, 2, true),    // 0: 9-bit digits, MATCH.ANY ranking: long keys (reference flow, 45 bits = 5 passes)
     LCGS_SWEEP64(512, 8, 9, 2, false),   // 1: 9-bit digits, ballot ranking: 15..18 key bits (8K frames)
     LCGS_SWEEP64(256, 20, 7, 2, false),  // 2: 7-bit digits, ballot ranking, 5120-pair tiles: <= 14 key bits (fused flow)
-    LCGS_SWEEP64_LEAN(256, 20, 7, 3),    // 3: as 2, upper key words + 16-bit ranks in registers, keys by LDGSTS: 3 CTAs/SM
 #ifdef LCGS_TUNING
-    LCGS_SWEEP64_LEAN(256, 20, 7, 2),    // 4
-    LCGS_SWEEP64_LEAN(256, 16, 7, 3),    // 5
-    LCGS_SWEEP64_LEAN(256, 16, 7, 4),    // 6
-    LCGS_SWEEP64_LEAN(512, 10, 7, 2),    // 7: 16 warps per CTA, 64 registers
-    LCGS_SWEEP64_LEAN(256, 24, 7, 2),    // 8
-    LCGS_SWEEP64(256, 12, 7, 4, false),  // 9: 3072-pair tiles, 4 CTAs/SM
-    LCGS_SWEEP64(256, 24, 7, 2, false),  // 10: 6144-pair tiles
+    LCGS_SWEEP64(256, 12, 7, 4, false),  // 3: same, 3072-pair tiles, 4 CTAs/SM
+    LCGS_SWEEP64(512, 8, 7, 2, true),    // 4: 7-bit digits, MATCH.ANY ranking (the earlier default)
+    LCGS_SWEEP64(256, 16, 7, 3, false),  // 5: 4096-pair tiles, 3 CTAs/SM (85 registers)
+    LCGS_SWEEP64(256, 24, 7, 2, false),  // 6: 6144-pair tiles
+    LCGS_SWEEP64(384, 14, 7, 2, false),  // 7: 5376-pair tiles, 12 warps per CTA
+    LCGS_SWEEP64(512, 10, 7, 2, false),  // 8: 5120-pair tiles, 16 warps per CTA (64 registers)
 #endif
 };
 // 32-bit depth keys of the per-Gaussian sort

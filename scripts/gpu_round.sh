@@ -39,7 +39,7 @@ except Exception as e:
 PY
 fi
 if [ "$a" = "ncufull" ]; then
-ncu --set full --clock-control none --import-source on -k "regex:blend_kernel|onesweep_pass|preprocess_fused|duplicate_keys_sorted|scan_compact|emit_big|tile_ranges|tile_order" -s 36 -c 13 -f -o gpurun_out/full_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-orbit > gpurun_out/ncu_full_$TAG.log 2>&1; echo ncufull rc=$?
+ncu --set full --clock-control none --import-source on -k "regex:blend_kernel|onesweep_pass|preprocess_fused|duplicate_keys_sorted|scan_compact|emit_big|tile_ranges|tile_order" -s 39 -c 13 -f -o gpurun_out/full_$TAG python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-orbit > gpurun_out/ncu_full_$TAG.log 2>&1; echo ncufull rc=$?
 python scripts/ncu_export.py gpurun_out/full_$TAG.ncu-rep gpurun_out/full_$TAG.csv | tail -1
 fi
 done

@@ -345,6 +345,17 @@ def test_heavy_tailed_tiles_and_huge_splats(lcgs, dev):
     assert lens.max() > 500
 
 
+def test_big_gaussians_take_the_piece_balanced_emission_path(lcgs, dev):
+    """Frames / bands of >= 12288 tiles expand Gaussians that cover more than 128 tiles in emit_big_kernel (pieces of 2048
+    instances, one CTA each) instead of in the warp that owns them; offsets, unsorted multiset, sorted lists, ranges and
+    image must not change.  2048 x 1536 = 128 x 96 tiles, scale_modifier 30: most instances come from such Gaussians."""
+    sc, pose = make_case("C3", 3000, 2048, 1536)
+    fr = _render_and_compare(lcgs, dev, sc, pose, 2048, 1536, scale_modifier=30.0, bg=(0.1, 0.2, 0.3))
+    big = fr.tiles_touched > 128
+    assert big.sum() > 200 and fr.tiles_touched[big].sum() > 0.5 * fr.num_rendered
+    assert (fr.tiles_touched > 2048).sum() > 10, "some Gaussians must span several pieces"
+
+
 @pytest.mark.parametrize("deg", [0, 1, 2])
 def test_fused_render_with_lower_sh_degree(lcgs, dev, deg):
     sc, pose = make_case("C3", 6000, 256, 160)
