@@ -611,6 +611,8 @@ class Bench:
         evc.record(consume_stream)
         self.barrier()
         ms = float(ev0.elapsed_time(ev1))
+        per_rank_render_ms = self.gather_counts(ms / steps)
+        consumer_ms = float(ev0.elapsed_time(evc)) / steps if rank == 0 else None
         if rank == 0:
             ms = max(ms, float(ev0.elapsed_time(evc)))
         ms_total = self.max_over_ranks(ms)
@@ -668,6 +670,8 @@ class Bench:
             "frames_per_second": total / (ms_total * 1e-3), "value": P * total / (ms_total * 1e-3), "unit": UNIT,
             "e2e_value": P * total / e2e_s, "e2e_frames_per_second": total / e2e_s, "e2e_ms_per_step": e2e_s / steps * 1e3,
             "consumed_frames_verified": verified, "flow_control_timeouts": int(timeouts),
+            "per_rank_render_stream_ms_per_step": [round(float(x), 4) for x in per_rank_render_ms],
+            "rank0_consumer_stream_ms_per_step": consumer_ms,
             "ring": "%d slots x %d ranks, float CHW + uint8 HWC image per slot (%.1f MB)" % (SLOTS, world, ring.frame_bytes / 1e6),
             "num_rendered_last_view": n_rendered, "stages_rank0": {k: round(v, 4) for k, v in stage_ms.items()},
             "gen_s": round(gen_s, 1), "upload_s": round(upload_s, 2),

@@ -16,6 +16,7 @@ try:
     d=json.loads(open('gpurun_out/bench_c4_n$N.json').read().strip().splitlines()[-1])
     v=d['view_sharding']
     print('C4 N', d['n_gpus'], 'ms/step', round(d['ms_per_step'],4), 'fps', round(d['frames_per_second'],1), 'G/s', round(d['value']/1e9,3), 'e2e fps', round(d['e2e']['frames_per_second'],1), 'verified', v['consumed_frames_verified'], 'timeouts', v['flow_control_timeouts'])
+    print(' per-rank render ms/step', v.get('per_rank_render_stream_ms_per_step'), 'consumer', v.get('rank0_consumer_stream_ms_per_step'))
 except Exception as e:
     print('parse failed', e)
 PY
@@ -31,7 +32,8 @@ import json
 try:
     d=json.loads(open('gpurun_out/bench_c5_n$N.json').read().strip().splitlines()[-1])
     t=d['tile_row_sharding']
-    print('C5 N', d['n_gpus'], 'ms/frame', round(d['ms_per_step'],4), 'e2e ms', round(d['e2e']['ms_per_step'],4), 'imbalance', t['band_imbalance_max_over_mean'], 'uniform', t['uniform_imbalance_max_over_mean'], 'verified', t['assembled_frame_equals_single_gpu_frame'], 'timeouts', t['flow_control_timeouts'])
+    print('C5 N', d['n_gpus'], 'ms/frame', round(d['ms_per_step'],4), 'e2e ms', round(d['e2e']['ms_per_step'],4), 'split', t['split'], 'time imbalance', round(t['time_imbalance_max_over_mean'],3), 'verified', t['assembled_frame_equals_single_gpu_frame'], 'timeouts', t['flow_control_timeouts'])
+    print(' band ms', t['band_ms_standalone'], [(x['split'], x['max_ms']) for x in t['splits_tried']])
     print(' per-rank ms', t['per_rank_ms_per_frame']); print(' stages rank0', t['per_rank_stage_ms'][0])
 except Exception as e:
     print('parse failed', e)
