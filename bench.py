@@ -66,6 +66,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-orbit", action="store_true", help="N = 1: skip the orbit_n1 leg")
     ap.add_argument("--capacity", type=int, default=None, help="instance list capacity L per rank")
+    ap.add_argument("--deliver", default="rgb8", choices=["rgb8", "float"],
+                    help="sharded workloads: what a rank writes into rank 0's ring -- rgb8: the app's final uint8 HWC image (3 B/pixel over "
+                         "NVLink, the float image stays local); float: the planar float32 image as well (15 B/pixel)")
     args = ap.parse_args()
     return args
 
@@ -556,13 +559,17 @@ class Bench:
         def vp_of(f):
             return lcgs.view_params(lcgs.make_camera(*scenes.orbit_pose(orbit_view(f, total)), W, H))
 
+        fl = args.deliver == "float"
         if world > 1:
-            ring = D.PeerFrameRing(dev, W, H, slots=SLOTS * world, rgb8=True)
+            ring = D.PeerFrameRing(dev, W, H, slots=SLOTS * world, rgb8=True, float_image=fl)
         else:
-            ring = _LocalRing(torch, dev, W, H, SLOTS, rgb8=True)
+            ring = _LocalRing(torch, dev, W, H, SLOTS, rgb8=True, float_image=fl)
         render_stream = torch.cuda.current_stream()
         consume_stream = torch.cuda.Stream()
-        n_words = 3 * W * H
+        # what rank 0 checksums: the delivered payload (32-bit words; the slot's padding behind a uint8 image stays zero)
+        n_words = 3 * W * H if fl else (3 * W * H + 3) // 4
+        payload = (lambda sl: ring.ptr(sl)) if fl else (lambda sl: ring.rgb8_ptr(sl))
+        local_img = r.img.data_ptr()
         sums = torch.zeros(warm + steps + 8, world, dtype=torch.int64, device="cuda") if rank == 0 else None
 
         gstep = [0]   # global step counter: sequence numbers continue across warm-up and timed region
@@ -574,7 +581,7 @@ class Bench:
             slot = slot_row * world + rank
             if g >= SLOTS:
                 ring.wait_consumed(slot, seq - 1, stream=render_stream)
-            r.set_target_ptr(ring.ptr(slot), ring.rgb8_ptr(slot))
+            r.set_target_ptr(ring.ptr(slot) if fl else local_img, ring.rgb8_ptr(slot))
             r.render_async(vp_of(s_local * world + rank), stream=render_stream)
             ring.signal_ready(slot, seq, stream=render_stream)
             self.launches += KERNELS_PER_FRAME + (2 if g >= SLOTS else 1)
@@ -583,7 +590,7 @@ class Bench:
                     sl = slot_row * world + w
                     ring.wait_ready(sl, seq, stream=consume_stream)
                     if host_out is None:
-                        dev.checksum_u32(ring.ptr(sl), n_words, sums[g, w:w + 1], stream=consume_stream)
+                        dev.checksum_u32(payload(sl), n_words, sums[g, w:w + 1], stream=consume_stream)
                     else:                           # end-to-end: the delivered uint8 image goes to the host
                         k = s_local * world + w
                         dev.check(dev.lib.lcgs_b200_peer_read_async(dev.ctx, ring.rgb8_ptr(sl), host_out[k % len(host_out)].data_ptr(),
@@ -622,12 +629,13 @@ class Bench:
         verified = None
         if rank == 0:
             local = torch.zeros(3 * W * H, dtype=torch.float32, device="cuda")
+            local8 = torch.zeros(4 * n_words + 256, dtype=torch.uint8, device="cuda")
             one = torch.zeros(1, dtype=torch.int64, device="cuda")
-            r.set_target_ptr(local.data_ptr(), 0)
+            r.set_target_ptr(local.data_ptr(), local8.data_ptr())
             verified = True
             for (s, w) in {(0, 0), (steps // 2, world - 1), (steps - 1, world // 2)}:
                 r.render_async(vp_of(s * world + w))
-                dev.checksum_u32(local.data_ptr(), n_words, one)
+                dev.checksum_u32((local if fl else local8).data_ptr(), n_words, one)
                 torch.cuda.synchronize()
                 verified &= bool(int(one.item()) == int(sums[first_g + s, w].item()))
             self.launches += 3 * (KERNELS_PER_FRAME + 1)
@@ -672,7 +680,8 @@ class Bench:
             "consumed_frames_verified": verified, "flow_control_timeouts": int(timeouts),
             "per_rank_render_stream_ms_per_step": [round(float(x), 4) for x in per_rank_render_ms],
             "rank0_consumer_stream_ms_per_step": consumer_ms,
-            "ring": "%d slots x %d ranks, float CHW + uint8 HWC image per slot (%.1f MB)" % (SLOTS, world, ring.frame_bytes / 1e6),
+            "delivered": "planar float32 + uint8 HWC image" if fl else "uint8 HWC image (the app's final product; the float image stays on the rendering rank)",
+            "ring": "%d slots x %d ranks, %.1f MB per slot" % (SLOTS, world, ring.frame_bytes / 1e6),
             "num_rendered_last_view": n_rendered, "stages_rank0": {k: round(v, 4) for k, v in stage_ms.items()},
             "gen_s": round(gen_s, 1), "upload_s": round(upload_s, 2),
         }
@@ -774,13 +783,16 @@ class Bench:
         assert n_band == int(band_counts[rank])
 
         SLOTS = 2
+        fl = args.deliver == "float"
         if world > 1:
-            ring = D.PeerFrameRing(dev, W, H, slots=SLOTS, rgb8=True, writers=world)
+            ring = D.PeerFrameRing(dev, W, H, slots=SLOTS, rgb8=True, writers=world, float_image=fl)
         else:
-            ring = _LocalRing(torch, dev, W, H, SLOTS, rgb8=True)
+            ring = _LocalRing(torch, dev, W, H, SLOTS, rgb8=True, float_image=fl)
         render_stream = torch.cuda.current_stream()
         consume_stream = torch.cuda.Stream()
-        n_words = 3 * W * H
+        n_words = 3 * W * H if fl else (3 * W * H + 3) // 4
+        payload = (lambda sl: ring.ptr(sl)) if fl else (lambda sl: ring.rgb8_ptr(sl))
+        local_img = r.img.data_ptr()
         sums = torch.zeros(warm + 2 * steps + 8, dtype=torch.int64, device="cuda") if rank == 0 else None
         gstep = [0]
 
@@ -790,7 +802,7 @@ class Bench:
             slot, seq = g % SLOTS, g // SLOTS + 1
             if g >= SLOTS:
                 ring.wait_consumed(slot, seq - 1, stream=render_stream)
-            r.set_target_ptr(ring.ptr(slot), ring.rgb8_ptr(slot))
+            r.set_target_ptr(ring.ptr(slot) if fl else local_img, ring.rgb8_ptr(slot))
             r.render_async(vp, stream=render_stream)
             ring.signal_ready(slot, seq, writer=rank, stream=render_stream)
             self.launches += KERNELS_PER_FRAME + (2 if g >= SLOTS else 1)
@@ -798,7 +810,7 @@ class Bench:
                 for w in range(world):
                     ring.wait_ready(slot, seq, writer=w, stream=consume_stream)
                 if host_out is None:
-                    dev.checksum_u32(ring.ptr(slot), n_words, sums[g:g + 1], stream=consume_stream)
+                    dev.checksum_u32(payload(slot), n_words, sums[g:g + 1], stream=consume_stream)
                 else:
                     dev.check(dev.lib.lcgs_b200_peer_read_async(dev.ctx, ring.rgb8_ptr(slot), host_out.data_ptr(), 3 * W * H,
                                                                 consume_stream.cuda_stream or None))
@@ -864,10 +876,12 @@ class Bench:
             if world > 1:
                 del r
                 torch.cuda.empty_cache()
-                rf, _ = self.make_renderer(sc, cfg, 260_000_000 if args.config == "C5" else args.capacity, rgb8=False)
+                rf, _ = self.make_renderer(sc, cfg, 260_000_000 if args.config == "C5" else args.capacity, rgb8=True)
+                full8 = torch.zeros(4 * n_words + 256, dtype=torch.uint8, device="cuda")
+                rf.set_target_ptr(rf.img.data_ptr(), full8.data_ptr())
                 n_full = rf.render(lcgs.make_camera(*pose, W, H))
                 one = torch.zeros(1, dtype=torch.int64, device="cuda")
-                dev.checksum_u32(rf.img.data_ptr(), n_words, one)
+                dev.checksum_u32((rf.img if fl else full8).data_ptr(), n_words, one)
                 torch.cuda.synchronize()
                 verified = bool(int(one.item()) == assembled) and n_full == int(sum(band_counts))
                 del rf
@@ -900,6 +914,7 @@ class Bench:
                 "splits_tried": [{"split": nm, "rows": [b1 - b0 for b0, b1 in bd], "instances": [int(c) for c in cn],
                                   "ms": [round(float(x), 4) for x in tm], "max_ms": round(max(tm), 4)} for nm, bd, cn, tm in tried],
                 "per_rank_ms_per_frame": [round(float(x), 4) for x in per_rank_ms], "per_rank_stage_ms": all_stage,
+                "delivered": "planar float32 + uint8 HWC image" if fl else "uint8 HWC image (the float strips stay on the rendering ranks)",
                 "assembled_frame_equals_single_gpu_frame": verified, "flow_control_timeouts": int(timeouts),
                 "hbm_floor_ms_per_gpu": "SURVEY.md 8d: 1.13 ms at 8 TB/s for an 8-way split (preprocess replicated)"},
             "stages": {k: {"ms": v} for k, v in all_stage[0].items()}, "sort_breakdown": sort_acc,
@@ -925,9 +940,9 @@ class _LocalRing:
     """The PeerFrameRing interface over plain local device memory (one GPU: nothing to map), so that the N = 1 number of
     a sharded workload runs the very same ring / flag / consumer code path."""
 
-    def __init__(self, torch, dev, W, H, slots, rgb8=True, writers=1):
+    def __init__(self, torch, dev, W, H, slots, rgb8=True, writers=1, float_image=True):
         self.dev, self.W, self.H, self.slots, self.writers = dev, W, H, slots, writers
-        self.img_bytes = 3 * W * H * 4
+        self.img_bytes = 3 * W * H * 4 if float_image else 0
         self.rgb8_bytes = ((3 * W * H + 255) // 256) * 256 if rgb8 else 0
         self.frame_bytes = ((self.img_bytes + self.rgb8_bytes + 255) // 256) * 256
         self.flags_offset = self.frame_bytes * slots

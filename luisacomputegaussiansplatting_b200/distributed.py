@@ -147,12 +147,15 @@ class PeerFrameRing:
         writer has its own ready flag per slot (`writer`)."""
 
     def __init__(self, device, width: int, height: int, slots: int, dst: int = 0, group=None, rgb8: bool = False,
-                 writers: int = 1):
+                 writers: int = 1, float_image: bool = True):
+        """float_image=False: slots hold only the uint8 image (the app's final product: 3 bytes per pixel cross NVLink
+        instead of 15); the planar float image then stays in the renderer's local buffer."""
         from . import lcgs
 
+        assert float_image or rgb8
         self.device = device
         self.W, self.H, self.slots, self.dst, self.group = width, height, slots, dst, group
-        self.img_bytes = 3 * width * height * 4
+        self.img_bytes = 3 * width * height * 4 if float_image else 0
         self.rgb8_bytes = ((3 * width * height + 255) // 256) * 256 if rgb8 else 0
         self.frame_bytes = self.img_bytes + self.rgb8_bytes          # a multiple of 4 (and of 16 for W*H % 4 == 0)
         self.frame_bytes = ((self.frame_bytes + 255) // 256) * 256
@@ -162,6 +165,7 @@ class PeerFrameRing:
         self.buf = lcgs.PeerBuffer(device, self.flags_offset + 4 * slots * (writers + 1) + 256, owner=dst, group=group)
 
     def ptr(self, slot: int) -> int:
+        """The slot's planar float image (its start; with float_image=False the slot starts with the uint8 image)."""
         assert 0 <= slot < self.slots
         return self.buf.ptr + slot * self.frame_bytes
 

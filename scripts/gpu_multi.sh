@@ -21,6 +21,19 @@ except Exception as e:
     print('parse failed', e)
 PY
 fi
+if [ "$a" = "c4float" ]; then
+timeout 900 $RUN --master-port 29514 bench.py --gpus $N --steps 20 --warmup 5 --deliver float > gpurun_out/bench_c4_float_n$N.json 2> gpurun_out/bench_c4_float_n$N.err; echo bench_c4_float rc=$?
+python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/bench_c4_float_n$N.json').read().strip().splitlines()[-1])
+    v=d['view_sharding']
+    print('C4 float N', d['n_gpus'], 'ms/step', round(d['ms_per_step'],4), 'fps', round(d['frames_per_second'],1), 'e2e fps', round(d['e2e']['frames_per_second'],1), 'verified', v['consumed_frames_verified'])
+    print(' per-rank render ms/step', v.get('per_rank_render_stream_ms_per_step'), 'consumer', v.get('rank0_consumer_stream_ms_per_step'))
+except Exception as e:
+    print('parse failed', e)
+PY
+fi
 if [ "$a" = "c4ref" ]; then
 timeout 900 $RUN --master-port 29513 bench.py --impl reference --gpus $N --steps 5 --warmup 1 > gpurun_out/bench_c4_ref_n$N.json 2> gpurun_out/bench_c4_ref_n$N.err; echo bench_c4_ref rc=$?; cut -c1-300 gpurun_out/bench_c4_ref_n$N.json
 fi
