@@ -462,7 +462,7 @@ size_t emit_ws_bytes(int P, size_t capacity)
 
 int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, int H, int num_rows,
                                  const SortedPairsU32& sorted, const uint2* rects, uint64_t* keys, uint32_t* vals,
-                                 size_t capacity, int row0, const SortDigits* digits, cudaStream_t s)
+                                 size_t capacity, int row0, const SortDigits* digits, cudaStream_t s, bool cleared)
 {
     if (P <= 0) return LCGS_B200_OK;
     // fused histograms need the digits to live in the tile id (key bits >= 32) and at most two passes
@@ -479,11 +479,19 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
     const uint32_t gy        = (uint32_t)(num_rows > 0 ? num_rows : (H + 15) / 16);
     const bool     exact_div = (unsigned long long)gx * gx * gy < 0x100000000ull;
     const uint32_t tiles     = (uint32_t)(((size_t)P + kEmitTile - 1) / kEmitTile);
-    int            rc        = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * sizeof(unsigned long long));
-    if (rc) return rc;
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->scan_ws.ptr, 0, (size_t)tiles * sizeof(unsigned long long), s));
-    uint32_t* ticket = ctx->d_scalars + LCGS_SCALAR_DUP_TICKET;
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, 3 * sizeof(uint32_t), s));  // ticket + the two big-list counters
+    static_assert(kEmitTile == 1024, "scan.cu: emit_status_words");
+    int                 rc;
+    uint32_t*           ticket = ctx->d_scalars + LCGS_SCALAR_DUP_TICKET;
+    unsigned long long* status;
+    if (cleared) {
+        // scan_frame_prepare: the emission's status words follow the scan's (2 per 2048 Gaussians) and are zero already
+        status = (unsigned long long*)ctx->scan_ws.ptr + 2 * (((size_t)P + 2047) / 2048);
+    } else {
+        if ((rc = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * sizeof(unsigned long long)))) return rc;
+        status = (unsigned long long*)ctx->scan_ws.ptr;
+        LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(status, 0, (size_t)tiles * sizeof(unsigned long long), s));
+        LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, 3 * sizeof(uint32_t), s));  // ticket + the two big-list counters
+    }
     // side lists of the big Gaussians: each holds more than `threshold` instances, so a frame within its list capacity
     // has at most capacity / (threshold + 1) of them (a frame that overflows is reported as such; entries beyond are dropped)
     BigLists big;
@@ -498,7 +506,7 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
     const uint32_t blocks     = tiles < max_blocks ? tiles : max_blocks;
     const bool big_path = (unsigned long long)gx * gy >= (unsigned long long)LCGS_TUNE_INT("LCGS_EMIT_BIG_MIN_TILES", (int)kBigPathMinTiles);
     auto kern = big_path ? duplicate_keys_sorted_kernel<true> : duplicate_keys_sorted_kernel<false>;
-    kern<<<blocks, kEmitThreads, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, sorted, rects, (unsigned long long*)ctx->scan_ws.ptr, ticket,
+    kern<<<blocks, kEmitThreads, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, sorted, rects, status, ticket,
                                          reinterpret_cast<unsigned long long*>(keys), vals, capacity, dg, exact_div, big);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     if (big_path) {
@@ -510,10 +518,10 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
 }
 
 int launch_ranges(lcgs_b200_ctx* ctx, const uint64_t* keys, size_t n_host, const uint32_t* d_n, size_t capacity,
-                  uint32_t* ranges, int num_tiles, cudaStream_t s)
+                  uint32_t* ranges, int num_tiles, cudaStream_t s, bool cleared)
 {
     if (num_tiles <= 0) return LCGS_B200_OK;
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), s));
+    if (!cleared) LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), s));
     const size_t bound = d_n ? capacity : n_host;
     if (bound == 0) return LCGS_B200_OK;
     LCGS_REQUIRE(ctx, (((uintptr_t)keys) & 15) == 0, "tile_ranges: keys must be 16-byte aligned");
@@ -593,6 +601,39 @@ int launch_checksum_u32(lcgs_b200_ctx* ctx, const void* data, size_t num_words, 
     checksum_u32_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(data), num_vec,
                                                          reinterpret_cast<const uint32_t*>(data) + num_vec * 4, (uint32_t)(num_words & 3),
                                                          reinterpret_cast<unsigned long long*>(out));
+    LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+    return LCGS_B200_OK;
+}
+
+// ---- one clear for everything a fused frame needs zeroed (ClearList, common.cuh) ---------------------------------
+__global__ void __launch_bounds__(256) frame_clear_kernel(const __grid_constant__ ClearList cl)
+{
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    for (int r = 0; r < cl.n; r++) {
+        uint32_t* const p     = static_cast<uint32_t*>(cl.ptr[r]);
+        const uint32_t  words = cl.words[r];
+        // 16-byte stores over the aligned middle, 4-byte stores for the (at most three-word) head and tail
+        const uint32_t head = (uint32_t)((16u - ((uintptr_t)p & 15u)) & 15u) / 4u;
+        const uint32_t h    = head < words ? head : words;
+        const uint32_t nvec = (words - h) / 4u;
+        uint4* const   v    = reinterpret_cast<uint4*>(p + h);
+        for (uint32_t k = gtid; k < nvec; k += gsize) v[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (gtid < h) p[gtid] = 0u;
+        const uint32_t tail0 = h + nvec * 4u;
+        if (gtid < words - tail0) p[tail0 + gtid] = 0u;
+    }
+}
+
+int launch_clear(lcgs_b200_ctx* ctx, const ClearList& cl, cudaStream_t s)
+{
+    if (cl.n == 0) return LCGS_B200_OK;
+    size_t words = 0;
+    for (int r = 0; r < cl.n; r++) words += cl.words[r];
+    size_t       blocks     = (words / 4 + 255) / 256;
+    const size_t max_blocks = (size_t)ctx->num_sms * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks == 0) blocks = 1;
+    frame_clear_kernel<<<(unsigned)blocks, 256, 0, s>>>(cl);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }

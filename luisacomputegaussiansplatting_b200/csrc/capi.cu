@@ -125,21 +125,28 @@ static int splat_tail(lcgs_b200_ctx* ctx, int P, const lcgs_b200_frame* fr, cons
     if (depth_ordered) {
         const OrderWs o = order_ws_views(ctx, P);
         SortDigits    dg32, dg64;
-        // Depth keys are stored relative to bits(0.2f) (kDepthKeyBase): 27 bits for any depth below
-        // 13107, so the fourth 9-bit pass normally skips itself.  The compaction kernel also fills the
-        // depth sort's digit histograms, the emission kernel those of the tile sort.
-        if ((rc = sort_prepare_u32(ctx, (size_t)P, 0, 32, &dg32, s))) return rc;
-        if ((rc = launch_scan_compact(ctx, fr->tiles_touched, fr->depth, P, fr->point_offsets, o.ckeys, o.cvals, d_n, d_m, &dg32, s)))
+        // Plan first: both sorts' geometry and workspace, the scan's and the emission's status words, tickets and the
+        // ranges buffer are known before the first kernel, so ONE kernel zeroes all of it.
+        // Depth keys are stored relative to bits(0.2f) (kDepthKeyBase): 27 bits for any depth below 13107, so the
+        // fourth 9-bit pass normally skips itself.  The compaction kernel also fills the depth sort's digit
+        // histograms, the emission kernel those of the tile sort.
+        ClearList cl;
+        if ((rc = sort_prepare_frame(ctx, (size_t)P, fr->list_capacity, g.end_bit, &dg32, &dg64, &cl))) return rc;
+        if ((rc = scan_frame_prepare(ctx, P, &cl))) return rc;
+        cl.add(ctx->d_scalars + LCGS_SCALAR_SCAN_TICKET, 10 * sizeof(uint32_t));  // scan ticket, 8 sort tickets, spare
+        cl.add(ctx->d_scalars + LCGS_SCALAR_DUP_TICKET, 3 * sizeof(uint32_t));    // emission ticket + big-list counters
+        cl.add(fr->ranges, (size_t)g.num_tiles * 2 * sizeof(uint32_t));
+        if ((rc = launch_clear(ctx, cl, s))) return rc;
+        if ((rc = launch_scan_compact(ctx, fr->tiles_touched, fr->depth, P, fr->point_offsets, o.ckeys, o.cvals, d_n, d_m, &dg32, s, true)))
             return rc;
         mark(ctx, s);
         const bool hist32 = dg32.hist && dg32.num_passes <= 4;
         SortedPairsU32 sorted;
         if ((rc = sort_run_u32(ctx, o.ckeys, o.skeys, o.cvals, o.svals, d_m, (size_t)P, hist32, &sorted, s))) return rc;
         mark(ctx, s);
-        if ((rc = sort_prepare_u64(ctx, fr->list_capacity, 32, g.end_bit, &dg64, s))) return rc;
         const bool hist64 = dg64.hist && dg64.num_passes >= 1 && dg64.num_passes <= 2;
         if ((rc = launch_duplicate_keys_sorted(ctx, d_m, P, g.W, g.H, g.row1 - g.row0, sorted, o.rects, fr->point_list_keys_unsorted,
-                                               fr->point_list_unsorted, fr->list_capacity, g.row0, hist64 ? &dg64 : nullptr, s)))
+                                               fr->point_list_unsorted, fr->list_capacity, g.row0, hist64 ? &dg64 : nullptr, s, true)))
             return rc;
         mark(ctx, s);
         if ((rc = sort_run_u64(ctx, fr->point_list_keys_unsorted, fr->point_list_keys, fr->point_list_unsorted,
@@ -160,7 +167,7 @@ static int splat_tail(lcgs_b200_ctx* ctx, int P, const lcgs_b200_frame* fr, cons
             return rc;
         mark(ctx, s);
     }
-    if ((rc = launch_ranges(ctx, fr->point_list_keys, 0, d_n, fr->list_capacity, fr->ranges, g.num_tiles, s))) return rc;
+    if ((rc = launch_ranges(ctx, fr->point_list_keys, 0, d_n, fr->list_capacity, fr->ranges, g.num_tiles, s, depth_ordered))) return rc;
     mark(ctx, s);
     // tile schedule (longest list first) + the frame's capacity check, made on the device against the count
     if ((rc = launch_tile_order(ctx, fr->ranges, g.num_tiles, d_n, fr->list_capacity, s))) return rc;

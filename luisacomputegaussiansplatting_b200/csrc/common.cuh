@@ -109,17 +109,38 @@ int tuning_env_int(const char* name, int fallback);
 #define LCGS_TUNE_INT(name, fallback) (fallback)
 #endif
 
+// Everything a fused frame needs zeroed before its first kernel -- digit histograms, look-back status words of the two
+// sorts, of the scan and of the emission, tickets, the ranges buffer -- collected while the frame is planned and cleared
+// by ONE kernel (nine cudaMemsetAsync nodes per frame cost ~25 us of a 1.5 ms frame).
+struct ClearList {
+    static constexpr int kMax = 8;
+    void*    ptr[kMax];
+    uint32_t words[kMax];  // 32-bit words; ptr 4-byte aligned
+    int      n = 0;
+    void add(void* p, size_t bytes)
+    {
+        if (bytes == 0 || n >= kMax) return;
+        ptr[n]   = p;
+        words[n] = (uint32_t)((bytes + 3) / 4);
+        n++;
+    }
+};
+int launch_clear(lcgs_b200_ctx* ctx, const ClearList& cl, cudaStream_t s);
+
 // stage launchers (one group per .cu); all enqueue on `s` and return an lcgs_b200_status
 int launch_preprocess_fused(lcgs_b200_ctx* ctx, const lcgs_b200_scene* sc, const lcgs_b200_view_params* vp,
                             const lcgs_b200_frame* fr, float4* records, uint2* rects, cudaStream_t s);
 struct SortDigits;
+// `cleared`: the status words (scan_ws) and the ticket have been zeroed by the frame's clear kernel (scan_frame_prepare)
 int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const float* depth, int P, uint32_t* offsets,
                         uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, const SortDigits* digits,
-                        cudaStream_t s);
+                        cudaStream_t s, bool cleared = false);
+// reserves the look-back status words of the scan+compaction and of the emission (disjoint) and lists them for clearing
+int scan_frame_prepare(lcgs_b200_ctx* ctx, int P, ClearList* cl);
 struct SortedPairsU32;
 int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P, int W, int H, int num_rows,
                                  const SortedPairsU32& sorted, const uint2* rects, uint64_t* keys, uint32_t* vals,
-                                 size_t capacity, int row0, const SortDigits* digits, cudaStream_t s);
+                                 size_t capacity, int row0, const SortDigits* digits, cudaStream_t s, bool cleared = false);
 // digit layout of a prepared sort, for kernels that accumulate its histograms while producing the keys
 struct SortDigits {
     uint32_t* hist;  // [num_passes][1 << radix_bits], zeroed
@@ -128,7 +149,9 @@ struct SortDigits {
     uint32_t  mask[kMaxSortPasses];
 };
 void sort_free_plans(lcgs_b200_ctx* ctx);
-int sort_prepare_u32(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s);
+// both sorts of the fused frame planned at once (depth sort of <= P Gaussians over 32 bits, tile sort of <= L instances over
+// key bits [32, end_bit)): one workspace reservation, disjoint status words and tickets, everything to zero listed in `cl`
+int sort_prepare_frame(lcgs_b200_ctx* ctx, size_t P, size_t L, int end_bit, SortDigits* dg32, SortDigits* dg64, ClearList* cl);
 // Where a u32 sort left its result: (keys, vals), or (alt_keys, alt_vals) when the last pass found all
 // its keys in digit 0 and skipped itself -- the case iff last_hist && *last_hist == n (device-side test).
 struct SortedPairsU32 {
@@ -137,7 +160,6 @@ struct SortedPairsU32 {
 __device__ __forceinline__ bool sorted_in_alt(const SortedPairsU32& r, uint32_t n) { return r.last_hist && __ldg(r.last_hist) == n; }
 int sort_run_u32(lcgs_b200_ctx* ctx, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
                  const uint32_t* d_n, size_t capacity, bool hist_ready, SortedPairsU32* res, cudaStream_t s);
-int sort_prepare_u64(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s);
 int sort_run_u64(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
                  const uint32_t* d_n, size_t capacity, bool hist_ready, cudaStream_t s);
 int launch_sh(lcgs_b200_ctx* ctx, int P, int deg, const float* cam_pos, const float* pos, const float* sh, float* color,
@@ -159,7 +181,7 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
                 uint32_t* vals_out, size_t n_host, const uint32_t* d_n, size_t capacity, int begin_bit, int end_bit,
                 cudaStream_t s);
 int launch_ranges(lcgs_b200_ctx* ctx, const uint64_t* keys, size_t n_host, const uint32_t* d_n, size_t capacity,
-                  uint32_t* ranges, int num_tiles, cudaStream_t s);
+                  uint32_t* ranges, int num_tiles, cudaStream_t s, bool cleared = false);
 int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32_t* ranges, const uint32_t* point_list,
                  const float4* records, const uint32_t* d_num_rendered, float* img, uint8_t* rgb8, int row0, int row1,
                  cudaStream_t s);

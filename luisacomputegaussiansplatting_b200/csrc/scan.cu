@@ -236,9 +236,22 @@ __global__ void __launch_bounds__(kScanThreads)
     }
 }
 
+// scan_ws of a fused frame: [2 x scan tiles][emission tiles] 64-bit status words
+static inline size_t scan_status_words(int P) { return 2 * (((size_t)(P > 0 ? P : 1) + kCompactTile - 1) / kCompactTile); }
+static inline size_t emit_status_words(int P) { return ((size_t)(P > 0 ? P : 1) + 1023) / 1024; }  // kEmitTile (binning.cu)
+
+int scan_frame_prepare(lcgs_b200_ctx* ctx, int P, ClearList* cl)
+{
+    const size_t bytes = (scan_status_words(P) + emit_status_words(P)) * sizeof(unsigned long long);
+    int          rc    = ws_reserve(ctx, ctx->scan_ws, bytes);
+    if (rc) return rc;
+    cl->add(ctx->scan_ws.ptr, bytes);
+    return LCGS_B200_OK;
+}
+
 int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const float* depth, int P, uint32_t* offsets,
                         uint32_t* ckeys, uint32_t* cvals, uint32_t* d_total, uint32_t* d_count, const SortDigits* digits,
-                        cudaStream_t s)
+                        cudaStream_t s, bool cleared)
 {
     SortDigits dg{};
     if (digits && digits->hist && digits->num_passes <= 4 && digits->radix_bits <= 9) dg = *digits;
@@ -250,11 +263,13 @@ int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const
     // 16-byte aligned buffers (any cudaMalloc'ed array) take the vector path, sub-allocated ones the scalar one
     const int vec_ok = ((((uintptr_t)tiles_touched) | ((uintptr_t)offsets) | ((uintptr_t)depth)) & 15) == 0;
     const uint32_t tiles = (uint32_t)(((size_t)P + kCompactTile - 1) / kCompactTile);
-    int            rc    = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * 2 * sizeof(unsigned long long));
-    if (rc) return rc;
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->scan_ws.ptr, 0, (size_t)tiles * 2 * sizeof(unsigned long long), s));
     uint32_t* ticket = ctx->d_scalars + LCGS_SCALAR_SCAN_TICKET;
-    LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
+    if (!cleared) {
+        int rc = ws_reserve(ctx, ctx->scan_ws, (size_t)tiles * 2 * sizeof(unsigned long long));
+        if (rc) return rc;
+        LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->scan_ws.ptr, 0, (size_t)tiles * 2 * sizeof(unsigned long long), s));
+        LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
+    }
     auto* st = (unsigned long long*)ctx->scan_ws.ptr;
     const uint32_t max_blocks = (uint32_t)ctx->num_sms * 6u;  // persistent: 6 x 256 threads per SM
     scan_compact_kernel<<<tiles < max_blocks ? tiles : max_blocks, kScanThreads, 0, s>>>(tiles_touched, depth, (uint32_t)P, tiles, offsets, ckeys, cvals, st,

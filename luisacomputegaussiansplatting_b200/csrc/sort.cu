@@ -509,16 +509,16 @@ struct SortPlan {
     SortPassInfo info;
     int          variant;
     size_t       bound, tiles;
-    uint32_t *   hist, *status, *tmp_vals;
+    uint32_t *   hist, *status, *tmp_vals, *ticket;
     KeyT*        tmp_keys;
 };
 
 // Pass geometry + workspace + zeroed histograms / look-back status / tickets.  After this call another
 // kernel may accumulate the digit histograms itself (plan.hist, layout [pass][1 << radix_bits]) and
 // launch_sort_t can be told to skip its own histogram kernel.
+// digit cut, kernel geometry and tile count of a sort over `bound` pairs; no workspace yet
 template <typename KeyT>
-static int sort_prepare_t(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, uint32_t* ticket, SortPlan<KeyT>* plan,
-                          cudaStream_t s, int hist_slot = 1)
+static int sort_plan_geometry(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortPlan<KeyT>* plan)
 {
     constexpr int kKeyBits = (int)sizeof(KeyT) * 8;
     LCGS_REQUIRE(ctx, begin_bit >= 0 && end_bit <= kKeyBits && begin_bit <= end_bit, "sort: bad bit range");
@@ -541,11 +541,34 @@ static int sort_prepare_t(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int e
     plan->bound   = bound;
     plan->tiles   = (bound + var.tile - 1) / var.tile;
     plan->hist    = nullptr;
+    plan->ticket  = ctx->d_scalars + LCGS_SCALAR_SORT_TICKET;
+    return LCGS_B200_OK;
+}
+
+template <typename KeyT>
+static size_t sort_status_bytes(const SortPlan<KeyT>& plan)
+{
+    if (plan.info.num_passes == 0 || plan.bound == 0) return 0;
+    const size_t b = (size_t)plan.info.num_passes * plan.tiles * ((size_t)1 << plan.info.radix_bits) * sizeof(uint32_t);
+    return (b + 255) & ~(size_t)255;
+}
+
+// Pass geometry + workspace + zeroed histograms / look-back status / tickets.  After this call another
+// kernel may accumulate the digit histograms itself (plan.hist, layout [pass][1 << radix_bits]) and
+// launch_sort_t can be told to skip its own histogram kernel.
+template <typename KeyT>
+static int sort_prepare_t(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, uint32_t* ticket, SortPlan<KeyT>* plan,
+                          cudaStream_t s, int hist_slot = 1)
+{
+    int rc = sort_plan_geometry<KeyT>(ctx, bound, begin_bit, end_bit, plan);
+    if (rc) return rc;
+    plan->ticket = ticket;
+    const SortPassInfo& info = plan->info;
     if (info.num_passes == 0 || bound == 0) return LCGS_B200_OK;
 
     size_t       off_status, off_keys, off_vals;
     const size_t bytes = sort_ws_layout(bound, sizeof(KeyT), &off_status, &off_keys, &off_vals);
-    int          rc    = ws_reserve(ctx, ctx->sort_ws, bytes);
+    rc                 = ws_reserve(ctx, ctx->sort_ws, bytes);
     if (rc) return rc;
     char* ws       = (char*)ctx->sort_ws.ptr;
     plan->hist     = (uint32_t*)(ws + (size_t)hist_slot * kHistSlotBytes);
@@ -555,7 +578,7 @@ static int sort_prepare_t(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int e
     // zero this sort's histograms + the look-back status (contiguous) and the tickets
     char* const zero_from = (char*)plan->hist;
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(zero_from, 0, (size_t)(ws + off_status - zero_from) +
-                                                           (size_t)info.num_passes * plan->tiles * (1u << rbits) * sizeof(uint32_t), s));
+                                                           (size_t)info.num_passes * plan->tiles * ((size_t)1 << info.radix_bits) * sizeof(uint32_t), s));
     LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, kMaxSortPasses * sizeof(uint32_t), s));
     return LCGS_B200_OK;
 }
@@ -651,19 +674,8 @@ int launch_sort(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out,
 }
 
 // ---- fused path: the kernel that PRODUCES the keys also accumulates the digit histograms ------------
-// sort_prepare_* zeroes the workspace and returns where the histograms live and how digits are cut;
+// sort_prepare_frame plans both sorts of a frame and returns where the histograms live and how digits are cut;
 // sort_run_* then launches only the onesweep passes.
-int sort_prepare_u32(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s)
-{
-    if (!ctx->plan32) ctx->plan32 = new SortPlan<uint32_t>();
-    auto& plan = *static_cast<SortPlan<uint32_t>*>(ctx->plan32);
-    int   rc   = sort_prepare_t<uint32_t>(ctx, bound, begin_bit, end_bit, ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, &plan, s, 0);
-    if (rc) return rc;
-    digits->hist = plan.hist; digits->num_passes = plan.info.num_passes; digits->radix_bits = plan.info.radix_bits;
-    for (int p = 0; p < kMaxSortPasses; p++) { digits->shift[p] = plan.info.shift[p]; digits->mask[p] = plan.info.mask[p]; }
-    return LCGS_B200_OK;
-}
-
 // Sorts (keys_a, vals_a) using (keys_b, vals_b) as the ping-pong partner; both pairs are scratch.  The
 // result is in res->keys/vals, or in res->alt_* when the last pass skipped itself (SortedPairsU32).
 int sort_run_u32(lcgs_b200_ctx* ctx, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
@@ -675,19 +687,8 @@ int sort_run_u32(lcgs_b200_ctx* ctx, uint32_t* keys_a, uint32_t* keys_b, uint32_
     res->vals = res->alt_vals = in_b ? vals_b : vals_a;
     res->last_hist = nullptr;
     if (plan.info.num_passes == 0) return LCGS_B200_OK;  // nothing to sort by: the input is the result
-    return launch_sort_t<uint32_t>(ctx, plan, keys_a, keys_b, vals_a, vals_b, 0, d_n, capacity,
-                                   ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, hist_ready, false, s, true, res, true);
-}
-
-int sort_prepare_u64(lcgs_b200_ctx* ctx, size_t bound, int begin_bit, int end_bit, SortDigits* digits, cudaStream_t s)
-{
-    if (!ctx->plan64) ctx->plan64 = new SortPlan<unsigned long long>();
-    auto& plan = *static_cast<SortPlan<unsigned long long>*>(ctx->plan64);
-    int   rc   = sort_prepare_t<unsigned long long>(ctx, bound, begin_bit, end_bit, ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, &plan, s);
-    if (rc) return rc;
-    digits->hist = plan.hist; digits->num_passes = plan.info.num_passes; digits->radix_bits = plan.info.radix_bits;
-    for (int p = 0; p < kMaxSortPasses; p++) { digits->shift[p] = plan.info.shift[p]; digits->mask[p] = plan.info.mask[p]; }
-    return LCGS_B200_OK;
+    return launch_sort_t<uint32_t>(ctx, plan, keys_a, keys_b, vals_a, vals_b, 0, d_n, capacity, plan.ticket, hist_ready, false, s, true,
+                                   res, true);
 }
 
 int sort_run_u64(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
@@ -696,7 +697,51 @@ int sort_run_u64(lcgs_b200_ctx* ctx, const uint64_t* keys_in, uint64_t* keys_out
     const auto& plan = *static_cast<const SortPlan<unsigned long long>*>(ctx->plan64);
     return launch_sort_t<unsigned long long>(ctx, plan, reinterpret_cast<const unsigned long long*>(keys_in),
                                              reinterpret_cast<unsigned long long*>(keys_out), vals_in, vals_out, 0, d_n, capacity,
-                                             ctx->d_scalars + LCGS_SCALAR_SORT_TICKET, hist_ready, true, s);
+                                             plan.ticket, hist_ready, true, s);
+}
+
+static void export_digits(const SortPassInfo& info, uint32_t* hist, SortDigits* digits)
+{
+    digits->hist = hist; digits->num_passes = info.num_passes; digits->radix_bits = info.radix_bits;
+    for (int p = 0; p < kMaxSortPasses; p++) { digits->shift[p] = info.shift[p]; digits->mask[p] = info.mask[p]; }
+}
+
+// layout: [hist slot 0][hist slot 1][status of the depth sort][status of the tile sort][tmp keys][tmp vals]; the part up to
+// the tmp buffers is one contiguous region to clear.  Tickets: depth sort SORT_TICKET + 0..3, tile sort SORT_TICKET + 4..7.
+int sort_prepare_frame(lcgs_b200_ctx* ctx, size_t P, size_t L, int end_bit, SortDigits* dg32, SortDigits* dg64, ClearList* cl)
+{
+    if (!ctx->plan32) ctx->plan32 = new SortPlan<uint32_t>();
+    if (!ctx->plan64) ctx->plan64 = new SortPlan<unsigned long long>();
+    auto& p32 = *static_cast<SortPlan<uint32_t>*>(ctx->plan32);
+    auto& p64 = *static_cast<SortPlan<unsigned long long>*>(ctx->plan64);
+    int   rc;
+    if ((rc = sort_plan_geometry<uint32_t>(ctx, P, 0, 32, &p32))) return rc;
+    if ((rc = sort_plan_geometry<unsigned long long>(ctx, L, 32, end_bit, &p64))) return rc;
+    LCGS_REQUIRE(ctx, p32.info.num_passes <= 4 && p64.info.num_passes <= 4, "sort: a fused frame's sorts have at most four passes each");
+    const size_t s32 = sort_status_bytes(p32), s64 = sort_status_bytes(p64);
+    const size_t off_status = 2 * kHistSlotBytes;
+    const size_t off_keys   = (off_status + s32 + s64 + 255) & ~(size_t)255;
+    const size_t off_vals   = (off_keys + L * sizeof(unsigned long long) + 255) & ~(size_t)255;
+    const size_t total      = (off_vals + L * sizeof(uint32_t) + 255) & ~(size_t)255;
+    if ((rc = ws_reserve(ctx, ctx->sort_ws, total))) return rc;
+    char* ws = (char*)ctx->sort_ws.ptr;
+    if (s32) {
+        p32.hist = (uint32_t*)ws;
+        p32.status = (uint32_t*)(ws + off_status);
+        p32.tmp_keys = nullptr; p32.tmp_vals = nullptr;  // the depth sort ping-pongs between its two caller-provided buffers
+    }
+    p32.ticket = ctx->d_scalars + LCGS_SCALAR_SORT_TICKET;
+    if (s64) {
+        p64.hist = (uint32_t*)(ws + kHistSlotBytes);
+        p64.status = (uint32_t*)(ws + off_status + s32);
+        p64.tmp_keys = (unsigned long long*)(ws + off_keys);
+        p64.tmp_vals = (uint32_t*)(ws + off_vals);
+    }
+    p64.ticket = ctx->d_scalars + LCGS_SCALAR_SORT_TICKET + 4;
+    export_digits(p32.info, p32.hist, dg32);
+    export_digits(p64.info, p64.hist, dg64);
+    cl->add(ws, off_status + s32 + s64);
+    return LCGS_B200_OK;
 }
 
 void sort_free_plans(lcgs_b200_ctx* ctx)
