@@ -152,14 +152,14 @@ __device__ __forceinline__ void emit_hist_update(const EmitHist& h, bool emit, u
 // 1080p frame, whose largest Gaussian covers about a thousand tiles.
 constexpr uint32_t kBigPathMinTiles = 12288;
 
-template <bool BIG>
-__global__ void __launch_bounds__(kEmitThreads, 5)
-    duplicate_keys_sorted_kernel(const uint32_t* __restrict__ d_m, uint32_t m_capacity, uint32_t gx, uint32_t row0,
-                                 const __grid_constant__ SortedPairsU32 sorted, const uint2* __restrict__ rects,
-                                 unsigned long long* status, uint32_t* ticket, unsigned long long* __restrict__ keys,
-                                 uint32_t* __restrict__ vals, size_t capacity, const __grid_constant__ SortDigits digits,
-                                 bool exact_div, const __grid_constant__ BigLists big)
+template <bool BIG, bool EXACT_DIV>
+__device__ __forceinline__ void duplicate_keys_sorted_body(const uint32_t* __restrict__ d_m, uint32_t m_capacity, uint32_t gx, uint32_t row0,
+                                                           const SortedPairsU32& sorted, const uint2* __restrict__ rects,
+                                                           unsigned long long* status, uint32_t* ticket,
+                                                           unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                           size_t capacity, const SortDigits& digits, const BigLists& big)
 {
+    constexpr bool exact_div = EXACT_DIV;  // index inside a rect -> (x, y) by multiply-high instead of a division
     // digit histograms of the tile bits of the emitted keys (two passes at most: the tile sort then skips
     // its histogram kernel).  Consecutive lanes emit consecutive tiles of one Gaussian, so the upper digit
     // is aggregated per run of equal digits.
@@ -173,8 +173,9 @@ __global__ void __launch_bounds__(kEmitThreads, 5)
     const unsigned FULL = 0xFFFFFFFFu;
     for (int k = tid; k < nbins; k += kEmitThreads) s_hist[k] = 0u;
     const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(s_hist);
-    const EmitHist eh{ hist_addr, hist_addr + (4u << digits.radix_bits), digits.mask[0], digits.mask[1],
-                       digits.shift[0] - 32, digits.shift[1] - 32, do_hist, digits.num_passes > 1 };
+    const int      sh0 = digits.shift[0] - 32, sh1 = digits.shift[1] - 32;
+    const uint32_t m0 = digits.mask[0], m1 = digits.mask[1], hist1_addr = hist_addr + (4u << digits.radix_bits);
+    const bool     two_digits = digits.num_passes > 1;
 
     uint32_t M = *d_m;
     if (M > m_capacity) M = m_capacity;
@@ -316,7 +317,23 @@ __global__ void __launch_bounds__(kEmitThreads, 5)
                     keys[dst] = ((unsigned long long)tile << 32) | (unsigned long long)o_dbits;
                     vals[dst] = o_idx;
                 }
-                emit_hist_update(eh, emit, tile, lane, le_mask);
+                if (do_hist) {
+                    if (emit) red_shared_add(hist_addr + (((tile >> sh0) & m0) << 2), 1u);
+                    if (two_digits) {
+                        // consecutive lanes emit consecutive tiles: runs of equal upper digits are counted by
+                        // their first lane (MATCH.ANY is slow); emitting lanes are a prefix of the warp
+                        const uint32_t d1      = (tile >> sh1) & m1;
+                        const uint32_t prev    = __shfl_up_sync(FULL, d1, 1);
+                        const bool     lead    = emit && (lane == 0 || prev != d1);
+                        const unsigned leaders = __ballot_sync(FULL, lead);
+                        const int      n_emit  = __popc(__ballot_sync(FULL, emit));
+                        if (lead) {
+                            const unsigned above = leaders & ~le_mask;
+                            const int      end   = above ? __ffs(above) - 1 : n_emit;
+                            red_shared_add(hist1_addr + (d1 << 2), (uint32_t)(end - lane));
+                        }
+                    }
+                }
             }
         }
     }
@@ -327,6 +344,30 @@ __global__ void __launch_bounds__(kEmitThreads, 5)
             if (c) atomicAdd(digits.hist + k, c);
         }
     }
+}
+
+// Two entry points over one body: the plain kernel takes no big-list parameters at all (with them in its parameter
+// block the compiler re-loaded kernel constants inside the expansion loop: +30 % instructions per step).
+template <bool EXACT_DIV>
+__global__ void __launch_bounds__(kEmitThreads)
+    duplicate_keys_sorted_kernel(const uint32_t* __restrict__ d_m, uint32_t m_capacity, uint32_t gx, uint32_t row0,
+                                 const __grid_constant__ SortedPairsU32 sorted, const uint2* __restrict__ rects,
+                                 unsigned long long* status, uint32_t* ticket, unsigned long long* __restrict__ keys,
+                                 uint32_t* __restrict__ vals, size_t capacity, const __grid_constant__ SortDigits digits)
+{
+    duplicate_keys_sorted_body<false, EXACT_DIV>(d_m, m_capacity, gx, row0, sorted, rects, status, ticket, keys, vals, capacity, digits,
+                                                 BigLists{});
+}
+
+template <bool EXACT_DIV>
+__global__ void __launch_bounds__(kEmitThreads, 5)
+    duplicate_keys_sorted_big_kernel(const uint32_t* __restrict__ d_m, uint32_t m_capacity, uint32_t gx, uint32_t row0,
+                                     const __grid_constant__ SortedPairsU32 sorted, const uint2* __restrict__ rects,
+                                     unsigned long long* status, uint32_t* ticket, unsigned long long* __restrict__ keys,
+                                     uint32_t* __restrict__ vals, size_t capacity, const __grid_constant__ SortDigits digits,
+                                     const __grid_constant__ BigLists big)
+{
+    duplicate_keys_sorted_body<true, EXACT_DIV>(d_m, m_capacity, gx, row0, sorted, rects, status, ticket, keys, vals, capacity, digits, big);
 }
 
 // One CTA per (entry, piece): kBigPiece consecutive instances of one big Gaussian, coalesced.
@@ -505,9 +546,14 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
     const uint32_t max_blocks = (uint32_t)ctx->num_sms * 6u;
     const uint32_t blocks     = tiles < max_blocks ? tiles : max_blocks;
     const bool big_path = (unsigned long long)gx * gy >= (unsigned long long)LCGS_TUNE_INT("LCGS_EMIT_BIG_MIN_TILES", (int)kBigPathMinTiles);
-    auto kern = big_path ? duplicate_keys_sorted_kernel<true> : duplicate_keys_sorted_kernel<false>;
-    kern<<<blocks, kEmitThreads, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, sorted, rects, status, ticket,
-                                         reinterpret_cast<unsigned long long*>(keys), vals, capacity, dg, exact_div, big);
+    auto* const k64 = reinterpret_cast<unsigned long long*>(keys);
+    if (big_path) {
+        auto kern = exact_div ? duplicate_keys_sorted_big_kernel<true> : duplicate_keys_sorted_big_kernel<false>;
+        kern<<<blocks, kEmitThreads, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, sorted, rects, status, ticket, k64, vals, capacity, dg, big);
+    } else {
+        auto kern = exact_div ? duplicate_keys_sorted_kernel<true> : duplicate_keys_sorted_kernel<false>;
+        kern<<<blocks, kEmitThreads, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, sorted, rects, status, ticket, k64, vals, capacity, dg);
+    }
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     if (big_path) {
         emit_big_kernel<<<max_blocks, kEmitThreads, 0, s>>>(gx, (uint32_t)row0, reinterpret_cast<unsigned long long*>(keys), vals,
