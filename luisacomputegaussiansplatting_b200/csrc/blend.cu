@@ -297,6 +297,285 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
     }
 }
 
+// ---- two pixels per lane: 8x8 patches, packed FP32 ------------------------------------------------
+// Same algorithm, other shape: four warps per tile, each owning an 8x8 patch, lane = pixels (x, y) and
+// (x, y + 4).  A Gaussian that hits the patch is fetched once for 64 pixels, and the per-pixel arithmetic
+// of the pair runs on Blackwell's packed FP32 instructions (FADD2 / FMUL2 / FFMA2: two IEEE binary32
+// operations per lane and issue slot, per-Gaussian operands broadcast with the .F32 operand form), so the
+// inner loop is ~41 issue slots per 64 pixels instead of 2 x 33.  On the C3 frame the 8x8 patches take
+// 6.77 M hit evaluations and 0.86 M segment walks where the 8x4 patches take 9.98 M and 1.62 M
+// (tests/tools/blend_model.py replays both schedules on the oracle frame).  Every pixel still sees the same
+// operations in the same order with the same roundings, so the image is bit-identical to blend_kernel's.
+constexpr int kB2Threads = 128;
+constexpr int kB2Warps   = kB2Threads / 32;
+
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 bcast2(float x) { return pack2(x, x); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// acc = a * b + acc in place (one register pair for the loop-carried accumulator: no copies)
+__device__ __forceinline__ void fma2_acc(f32x2& acc, f32x2 a, f32x2 b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+// (ca, cb) += (wa, wb) * e, the accumulators living in two scalar registers
+__device__ __forceinline__ void fma2_acc_s(float& ca, float& cb, float wa, float wb, float e)
+{
+    asm("{\n\t.reg .b64 c, w, x;\n\tmov.b64 c, {%0, %1};\n\tmov.b64 w, {%2, %3};\n\tmov.b64 x, {%4, %4};\n\t"
+        "fma.rn.f32x2 c, w, x, c;\n\tmov.b64 {%0, %1}, c;\n\t}"
+        : "+f"(ca), "+f"(cb)
+        : "f"(wa), "f"(wb), "f"(e));
+}
+// 1 << pos without a constant register (BMSK)
+__device__ __forceinline__ unsigned bit_at(int pos)
+{
+    unsigned r;
+    asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(r) : "r"(pos));
+    return r;
+}
+// index of the highest set bit (FLO), x != 0
+__device__ __forceinline__ int top_bit(unsigned x)
+{
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+// CPT = candidates per thread and round (1 or 2): rounds of 128 * CPT list entries, 4 * CPT segments
+template <int MIN_CTAS, int CPT>
+__global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
+    blend2_kernel(int W, int H, uint32_t gx, uint32_t row0, float bg0, float bg1, float bg2,
+                  const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
+                  const uint32_t* __restrict__ point_list, const float4* __restrict__ records,
+                  const uint32_t* __restrict__ d_num_rendered /* non-null: apply quirk Q10 */, float* __restrict__ img,
+                  uint8_t* __restrict__ rgb8)
+{
+    if (d_num_rendered && *d_num_rendered == 0u) return;  // Q10, whole frames only (see blend_kernel)
+
+    constexpr int kB2Round = kB2Threads * CPT, kB2Segs = kB2Round / 32;
+    __shared__ float4   s_rec[2][3][kB2Round];  // [buffer][plane][slot], planes as in blend_kernel
+    __shared__ uint32_t s_cnt[2][kB2Segs];
+
+    const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL    = 0xFFFFFFFFu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t sbase   = (uint32_t)__cvta_generic_to_shared(&s_rec[0][0][0]);
+    constexpr uint32_t kPlane = kB2Round * 16u, kBuf = 3u * kPlane;
+
+    const uint32_t tile    = __ldg(order + blockIdx.x);  // band-local tile id, longest lists first
+    const uint32_t tile_by = tile / gx, tile_bx = tile - tile_by * gx;
+    const int tile_x0 = (int)tile_bx * 16, tile_y0 = (int)(row0 + tile_by) * 16;
+    const int patch_x0 = tile_x0 + (warp & 1) * 8, patch_y0 = tile_y0 + (warp >> 1) * 8;
+    const int px = patch_x0 + (lane & 7);
+    const int pya = patch_y0 + (lane >> 3), pyb = pya + 4;
+    const bool  in_a = px < W && pya < H, in_b = px < W && pyb < H;
+    const float pxf  = (float)px;                                  // no half-pixel offset (Q2)
+    const f32x2 npy2 = pack2(-(float)pya, -(float)pyb);            // my - py == my + (-py), exactly
+    const float tx0 = (float)tile_x0, ty0 = (float)tile_y0, tx1 = (float)(tile_x0 + 15), ty1 = (float)(tile_y0 + 15);
+
+    const uint2    range = __ldg(ranges + tile);
+    const uint32_t len   = range.y > range.x ? range.y - range.x : 0u;
+    const uint32_t nrounds = (len + kB2Round - 1) / kB2Round;
+
+    // T < 0 marks a finished pixel, as in blend_kernel
+    float Ta = in_a ? 1.0f : -1.0f, Tb = in_b ? 1.0f : -1.0f;
+    float c0a = 0.0f, c0b = 0.0f, c1a = 0.0f, c1b = 0.0f, c2a = 0.0f, c2b = 0.0f;
+
+    // candidate j (0, 1) of a thread is entry j * 128 + tid of the round: warp w's j-th ballot fills segment j * 4 + w,
+    // so segment s holds entries [32 s, 32 s + 32) and the consumers meet the list in order
+    auto produce = [&](uint32_t buf, int j, bool valid, const float4& a, const float4& b, const float4& c) {
+        const bool     keep = valid && !cull_rect_fast(a.x, a.y, a.z, a.w, b.x, b.y, b.w, c.w, tx0, ty0, tx1, ty1);
+        const unsigned kept = __ballot_sync(FULL, keep);
+        const uint32_t seg  = (uint32_t)(j * kB2Warps + warp);
+        if (keep) {
+            const uint32_t slot = seg * 32 + 31 - __popc(kept & lt_mask);  // filled from the top (FLO walk)
+            const uint32_t addr = sbase + buf * kBuf + slot * 16u;
+            sts128(addr, a);
+            sts128(addr + kPlane, b);
+            sts128(addr + 2u * kPlane, c);
+        }
+        if (lane == 0) s_cnt[buf][seg] = __popc(kept);
+    };
+
+    float4   ra0, rb0, rc0, ra1, rb1, rc1;
+    uint32_t next_id0 = 0, next_id1 = 0;
+    {
+        const bool v0 = (uint32_t)tid < len, v1 = CPT == 2 && (uint32_t)tid + kB2Threads < len;
+        if (v0) {
+            const float4* rec = records + (size_t)__ldg(point_list + range.x + tid) * kRecordFloat4s;
+            ra0 = __ldg(rec); rb0 = __ldg(rec + 1); rc0 = __ldg(rec + 2);
+        }
+        if (v1) {
+            const float4* rec = records + (size_t)__ldg(point_list + range.x + kB2Threads + tid) * kRecordFloat4s;
+            ra1 = __ldg(rec); rb1 = __ldg(rec + 1); rc1 = __ldg(rec + 2);
+        }
+        if (kB2Round + (uint32_t)tid < len) next_id0 = __ldg(point_list + range.x + kB2Round + tid);
+        if (CPT == 2 && kB2Round + kB2Threads + (uint32_t)tid < len) next_id1 = __ldg(point_list + range.x + kB2Round + kB2Threads + tid);
+        produce(0u, 0, v0, ra0, rb0, rc0);
+        if (CPT == 2) produce(0u, 1, v1, ra1, rb1, rc1);
+    }
+    __syncthreads();
+
+    const f32x2 one2 = bcast2(1.0f), l2e2 = bcast2(1.4426950408889634f);
+
+    for (uint32_t r = 0; r < nrounds; r++) {
+        const uint32_t buf = r & 1u;
+        // ---- issue the gathers of round r+1 ---------------------------------------------------------------
+        const uint32_t nidx0 = (r + 1u) * kB2Round + tid, nidx1 = nidx0 + kB2Threads;
+        const bool     nv0 = nidx0 < len, nv1 = CPT == 2 && nidx1 < len;
+        if (nv0) {
+            const float4* rec = records + (size_t)next_id0 * kRecordFloat4s;
+            ra0 = __ldg(rec); rb0 = __ldg(rec + 1); rc0 = __ldg(rec + 2);
+        }
+        if (nv1) {
+            const float4* rec = records + (size_t)next_id1 * kRecordFloat4s;
+            ra1 = __ldg(rec); rb1 = __ldg(rec + 1); rc1 = __ldg(rec + 2);
+        }
+        if (nidx0 + kB2Round < len) next_id0 = __ldg(point_list + range.x + nidx0 + kB2Round);
+        if (CPT == 2 && nidx1 + kB2Round < len) next_id1 = __ldg(point_list + range.x + nidx1 + kB2Round);
+
+        // ---- consume round r -------------------------------------------------------------------------------
+        bool da = Ta < 0.0f, db = Tb < 0.0f;
+        if (!__all_sync(FULL, da && db)) {
+            const uint32_t abase = sbase + buf * kBuf;
+            // bounding box of the pixels of the patch that are still accumulating
+            const unsigned lx = (unsigned)(lane & 7), ly = (unsigned)(lane >> 3);
+            const unsigned ax = (da && db) ? 255u : lx, bx = (da && db) ? 0u : lx;
+            const unsigned ay = !da ? ly : (!db ? ly + 4u : 255u), by = !db ? ly + 4u : (!da ? ly : 0u);
+            const float wx0 = (float)(patch_x0 + (int)__reduce_min_sync(FULL, ax));
+            const float wy0 = (float)(patch_y0 + (int)__reduce_min_sync(FULL, ay));
+            const float wx1 = (float)(patch_x0 + (int)__reduce_max_sync(FULL, bx));
+            const float wy1 = (float)(patch_y0 + (int)__reduce_max_sync(FULL, by));
+#pragma unroll 1
+            for (int seg = 0; seg < kB2Segs; seg++) {
+                const uint32_t cnt     = s_cnt[buf][seg];
+                const uint32_t segbase = abase + seg * 512u;
+                bool           hit     = false;
+                if ((uint32_t)lane + cnt >= 32u) {
+                    const float4 ga = lds128(segbase + lane * 16u);
+                    const float4 gb = lds128(segbase + kPlane + lane * 16u);
+                    const float  rx = lds32(segbase + 2u * kPlane + lane * 16u + 12u);
+                    hit             = !cull_rect_fast(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.w, rx, wx0, wy0, wx1, wy1);
+                }
+                unsigned hits = __ballot_sync(FULL, hit);
+                if (hits) do {
+                    const int      top  = top_bit(hits);
+                    const uint32_t addr = segbase + top * 16u;
+                    hits ^= bit_at(top);
+                    const float4 ea = lds128(addr);
+                    const float4 eb = lds128(addr + kPlane);
+                    const float4 ec = lds128(addr + 2u * kPlane);
+                    // blend_power(a, b, c, dx, dy) = fma(b*dx, dy, fma(a*dx, dx, (c*dy)*dy)) for both pixels; dx is shared
+                    const float dx   = ea.x - pxf;
+                    const float adx  = ea.z * dx, bdx = ea.w * dx;
+                    const f32x2 dy2  = add2(bcast2(ea.y), npy2);
+                    const f32x2 cdy2 = mul2(bcast2(eb.x), dy2);
+                    const f32x2 in2  = fma2(bcast2(adx), bcast2(dx), mul2(cdy2, dy2));
+                    const f32x2 pw2  = fma2(bcast2(bdx), dy2, in2);
+                    float pwa, pwb;
+                    unpack2(pw2, pwa, pwb);
+                    const bool oka = !(pwa > 0.0f) && !(pwa < eb.y);  // shader.cpp:257,259
+                    const bool okb = !(pwb > 0.0f) && !(pwb < eb.y);
+                    // alpha = min(0.99, 2^(power * log2(e) + log2(opacity)))
+                    float xa, xb;
+                    unpack2(fma2(pw2, l2e2, bcast2(eb.z)), xa, xb);
+                    const float alpa = fminf(0.99f, ex2_ftz(xa)), alpb = fminf(0.99f, ex2_ftz(xb));
+                    const f32x2 al2  = pack2(alpa, alpb);
+                    const f32x2 T2   = pack2(Ta, Tb);
+                    float tta, ttb, wa, wb;
+                    unpack2(mul2(T2, sub2(one2, al2)), tta, ttb);  // T * (1 - alpha): < 0 for a finished pixel
+                    unpack2(mul2(T2, al2), wa, wb);
+                    const bool bla = oka && !(tta < 0.0001f), blb = okb && !(ttb < 0.0001f);  // shader.cpp:261-265
+                    const float wsa = bla ? wa : 0.0f, wsb = blb ? wb : 0.0f;
+                    fma2_acc_s(c0a, c0b, wsa, wsb, ec.x);
+                    fma2_acc_s(c1a, c1b, wsa, wsb, ec.y);
+                    fma2_acc_s(c2a, c2b, wsa, wsb, ec.z);
+                    Ta = oka ? (bla ? tta : -fabsf(Ta)) : Ta;
+                    Tb = okb ? (blb ? ttb : -fabsf(Tb)) : Tb;
+                } while (hits);
+                da = Ta < 0.0f;
+                db = Tb < 0.0f;
+                if (__all_sync(FULL, da && db)) break;
+            }
+        }
+
+        // ---- produce round r+1 into the other buffer --------------------------------------------------------
+        if (r + 1u < nrounds) {
+            produce(buf ^ 1u, 0, nv0, ra0, rb0, rc0);
+            if (CPT == 2) produce(buf ^ 1u, 1, nv1, ra1, rb1, rc1);
+        }
+        if (__syncthreads_and(Ta < 0.0f && Tb < 0.0f)) break;
+    }
+
+    Ta = fabsf(Ta);
+    Tb = fabsf(Tb);
+    const float va0 = __fmaf_rn(bg0, Ta, c0a), va1 = __fmaf_rn(bg1, Ta, c1a), va2 = __fmaf_rn(bg2, Ta, c2a);
+    const float vb0 = __fmaf_rn(bg0, Tb, c0b), vb1 = __fmaf_rn(bg1, Tb, c1b), vb2 = __fmaf_rn(bg2, Tb, c2b);
+    const size_t plane = (size_t)W * (size_t)H;
+    if (in_a) {
+        const size_t pix = (size_t)px + (size_t)W * (size_t)pya;
+        img[pix] = va0; img[pix + plane] = va1; img[pix + 2 * plane] = va2;
+    }
+    if (in_b) {
+        const size_t pix = (size_t)px + (size_t)W * (size_t)pyb;
+        img[pix] = vb0; img[pix + plane] = vb1; img[pix + 2 * plane] = vb2;
+    }
+    if (rgb8) {
+        // the app's post-process as in blend_kernel: staged in shared memory, 32-byte runs per warp instruction
+        unsigned char* const s_u8 = reinterpret_cast<unsigned char*>(&s_rec[0][0][0]);
+        __syncthreads();
+        auto u8 = [](float v) { return (unsigned char)min(__float2uint_rz(v * 255.0f), 255u); };
+        if (in_a) {
+            const int o = ((pya - tile_y0) * 16 + (px - tile_x0)) * 3;
+            s_u8[o] = u8(va0); s_u8[o + 1] = u8(va1); s_u8[o + 2] = u8(va2);
+        }
+        if (in_b) {
+            const int o = ((pyb - tile_y0) * 16 + (px - tile_x0)) * 3;
+            s_u8[o] = u8(vb0); s_u8[o + 1] = u8(vb1); s_u8[o + 2] = u8(vb2);
+        }
+        __syncthreads();
+        const int cols = min(16, W - tile_x0) * 3;
+#pragma unroll
+        for (int k = tid; k < 16 * 48; k += kB2Threads) {
+            const int row = k / 48, col = k - row * 48, y = tile_y0 + row;
+            if (y < H && col < cols) rgb8[((size_t)(H - 1 - y) * (size_t)W + (size_t)tile_x0) * 3 + col] = s_u8[k];
+        }
+    }
+}
+
 // Display::_transpose_shader (app/display.cpp:30-39): planar CHW float -> RGBA8 unorm framebuffer, no flip.
 __global__ void __launch_bounds__(256) transpose_rgba8_kernel(int n, const float* __restrict__ img, uchar4* __restrict__ rgba)
 {
@@ -331,16 +610,38 @@ int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32
     const uint32_t num_tiles = gx * (uint32_t)(row1 - row0);
     // Q10 applies to a whole frame only (see the kernel)
     const bool whole = row0 == 0 && row1 == (int)gy;
-    // 48 registers -> 5 CTAs per SM (measured best of 4 / 5 / 6 / 8)
-    auto kern = blend_kernel<5>;
+    const uint2*    rg  = reinterpret_cast<const uint2*>(ranges);
+    const uint32_t* ord = (const uint32_t*)ctx->tile_order_ws.ptr;
+    const uint32_t* q10 = whole ? d_num_rendered : nullptr;
+    // two pixels per lane, 4 warps per tile; 72 registers -> 7 CTAs per SM (measured: 6 -> 0.489, 7 -> 0.487, 8 (64 registers,
+    // spills) -> 0.630, 10 -> 0.739 ms on the C3 frame)
+    auto kern2 = blend2_kernel<7, 2>;
 #ifdef LCGS_TUNING
-    const int occ = LCGS_TUNE_INT("LCGS_BLEND_OCC", 5);
-    if (occ == 4) kern = blend_kernel<4>;
-    if (occ == 6) kern = blend_kernel<6>;
+    const int occ2 = LCGS_TUNE_INT("LCGS_BLEND2_OCC", 7), cpt = LCGS_TUNE_INT("LCGS_BLEND2_CPT", 2);
+    if (cpt == 2) {
+        if (occ2 == 4) kern2 = blend2_kernel<4, 2>;
+        if (occ2 == 5) kern2 = blend2_kernel<5, 2>;
+        if (occ2 == 6) kern2 = blend2_kernel<6, 2>;
+        if (occ2 == 8) kern2 = blend2_kernel<8, 2>;
+    } else {
+        kern2 = blend2_kernel<8, 1>;
+        if (occ2 == 6) kern2 = blend2_kernel<6, 1>;
+        if (occ2 == 7) kern2 = blend2_kernel<7, 1>;
+        if (occ2 == 9) kern2 = blend2_kernel<9, 1>;
+        if (occ2 == 10) kern2 = blend2_kernel<10, 1>;
+    }
+    if (LCGS_TUNE_INT("LCGS_BLEND_P2", 1) == 0) {
+        // the one-pixel-per-lane kernel (8x4 patches, 48 registers -> 5 CTAs per SM), kept for A/B runs
+        auto      kern = blend_kernel<5>;
+        const int occ  = LCGS_TUNE_INT("LCGS_BLEND_OCC", 5);
+        if (occ == 4) kern = blend_kernel<4>;
+        if (occ == 6) kern = blend_kernel<6>;
+        kern<<<num_tiles, kBlendThreads, 0, s>>>(W, H, gx, (uint32_t)row0, bg[0], bg[1], bg[2], rg, ord, point_list, records, q10, img, rgb8);
+        LCGS_CUDA_CHECK(ctx, cudaGetLastError());
+        return LCGS_B200_OK;
+    }
 #endif
-    kern<<<num_tiles, kBlendThreads, 0, s>>>(W, H, gx, (uint32_t)row0, bg[0], bg[1], bg[2], reinterpret_cast<const uint2*>(ranges),
-                                             (const uint32_t*)ctx->tile_order_ws.ptr, point_list, records,
-                                             whole ? d_num_rendered : nullptr, img, rgb8);
+    kern2<<<num_tiles, kB2Threads, 0, s>>>(W, H, gx, (uint32_t)row0, bg[0], bg[1], bg[2], rg, ord, point_list, records, q10, img, rgb8);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
     return LCGS_B200_OK;
 }
