@@ -615,7 +615,7 @@ int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32
     const uint32_t* q10 = whole ? d_num_rendered : nullptr;
     // two pixels per lane, 4 warps per tile; 72 registers -> 7 CTAs per SM (measured: 6 -> 0.489, 7 -> 0.487, 8 (64 registers,
     // spills) -> 0.630, 10 -> 0.739 ms on the C3 frame)
-    auto kern2 = blend2_kernel<7, 2>;
+    auto kern2 = blend2_kernel<8, 1>;
 #ifdef LCGS_TUNING
     const int occ2 = LCGS_TUNE_INT("LCGS_BLEND2_OCC", 7), cpt = LCGS_TUNE_INT("LCGS_BLEND2_CPT", 2);
     if (cpt == 2) {
