@@ -1,27 +1,30 @@
 // blend.cu -- stage 5b: per-tile front-to-back alpha blending.
 // Replaces m_forward_render_shader (lcgs/src/gs_tile_splatter/shader.cpp:171-288).
 //
-// One 256-thread CTA per 16x16 tile; each warp owns an 8x4 pixel patch.  The tile's depth-sorted
-// list is consumed in rounds of 256 candidates through a double-buffered shared-memory stage:
+// One 128-thread CTA per 16x16 tile; each warp owns an 8x8 pixel patch, each lane two pixels of it
+// (blend2_kernel).  The tile's depth-sorted list is consumed in rounds of 128 candidates through a
+// double-buffered shared-memory stage:
 //   produce (round r+1): every thread gathers one Gaussian's packed 48-byte record (pixel mean,
 //      pre-scaled conic, alpha-test threshold, opacity, colour), tests it against the TILE
 //      rectangle with cull_rect_fast(), and each warp compacts its survivors, order preserved, into its
 //      own 32-slot segment (ballot + popc; no block-wide prefix, no extra barrier);
-//   consume (round r): each warp walks the 8 segments; per segment one lane per survivor tests it
-//      against the warp's 8x4 PATCH, and only the ballot's set bits are evaluated, all 32 pixels on
-//      the same Gaussian with broadcast LDS.128.
+//   consume (round r): each warp walks the 4 segments; per segment one lane per survivor tests it
+//      against the bounding box of the warp's unfinished pixels, and only the ballot's set bits are
+//      evaluated, all 64 pixels on the same Gaussian with broadcast LDS.128 and packed FP32 arithmetic.
 // The global gathers of round r+1 are in flight while round r is blended, and there is ONE
 // __syncthreads per round (it also carries the block-wide "every pixel saturated" vote).
 // cull_rect_fast() (lcgs_math.cuh; branch-free, its two divisions precomputed per Gaussian in the
 // record) is conservative with respect to the per-pixel float evaluation, so culling only removes
-// pairs the alpha test would have skipped: on the C3 scene 42 % of the
-// (Gaussian, tile) instances binned by the reference's loose rect never touch their tile and 78 %
-// of the (Gaussian, patch) pairs are empty -- the reference evaluates all of them for 256 pixels.
+// pairs the alpha test would have skipped: on the C3 scene 42 % of the (Gaussian, tile) instances
+// binned by the reference's loose rect never touch their tile -- the reference evaluates all of them
+// for 256 pixels.
 // Other differences that do not change results: colour is staged with the batch instead of fetched
 // from global memory per contributing pair (shader.cpp:268-269); the alpha >= 1/255 test is a
 // compare against a per-Gaussian power threshold, so no exp is needed to reject; the tile stops as
 // soon as every pixel has saturated (the reference keeps loading and barrier-ing until the list
 // ends, shader.cpp:226-277).
+// blend_kernel (one pixel per lane, 8 warps x 8x4 patches) is the kernel blend2_kernel replaced; it is
+// compiled into the -DLCGS_TUNING library only, for A/B runs.
 //
 // Compute-bound (FP32 issue + shared memory), not HBM-bound; HBM side is 4 B id + 48 B record per
 // instance (mostly L2 hits) + 12 B per pixel.
@@ -29,8 +32,10 @@
 
 namespace lcgs_b200 {
 
+#ifdef LCGS_TUNING
 constexpr int kBlendThreads = 256;
 constexpr int kBlendWarps   = kBlendThreads / 32;
+#endif
 
 __device__ __forceinline__ float4 lds128(uint32_t addr)
 {
@@ -122,6 +127,7 @@ __global__ void __launch_bounds__(kOrderThreads)
     }
 }
 
+#ifdef LCGS_TUNING  // the one-pixel-per-lane kernel blend2_kernel replaced; built into the tuning library only, for A/B runs
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
     blend_kernel(int W, int H, uint32_t gx, uint32_t row0, float bg0, float bg1, float bg2,
@@ -296,6 +302,8 @@ __global__ void __launch_bounds__(kBlendThreads, MIN_CTAS)
         }
     }
 }
+
+#endif  // LCGS_TUNING
 
 // ---- two pixels per lane: 8x8 patches, packed FP32 ------------------------------------------------
 // Same algorithm, other shape: four warps per tile, each owning an 8x8 patch, lane = pixels (x, y) and
@@ -491,14 +499,9 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
                     hit             = !cull_rect_fast(ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.w, rx, wx0, wy0, wx1, wy1);
                 }
                 unsigned hits = __ballot_sync(FULL, hit);
-                if (hits) do {
-                    const int      top  = top_bit(hits);
-                    const uint32_t addr = segbase + top * 16u;
-                    hits ^= bit_at(top);
-                    const float4 ea = lds128(addr);
-                    const float4 eb = lds128(addr + kPlane);
-                    const float4 ec = lds128(addr + 2u * kPlane);
-                    // blend_power(a, b, c, dx, dy) = fma(b*dx, dy, fma(a*dx, dx, (c*dy)*dy)) for both pixels; dx is shared
+                // one Gaussian on this lane's two pixels; blend_power(a, b, c, dx, dy) = fma(b*dx, dy, fma(a*dx, dx, (c*dy)*dy)),
+                // dx is shared by the pair
+                auto evaluate = [&](const float4& ea, const float4& eb, const float4& ec) {
                     const float dx   = ea.x - pxf;
                     const float adx  = ea.z * dx, bdx = ea.w * dx;
                     const f32x2 dy2  = add2(bcast2(ea.y), npy2);
@@ -525,7 +528,18 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
                     fma2_acc_s(c2a, c2b, wsa, wsb, ec.z);
                     Ta = oka ? (bla ? tta : -fabsf(Ta)) : Ta;
                     Tb = okb ? (blb ? ttb : -fabsf(Tb)) : Tb;
-                } while (hits);
+                };
+                // (requesting the next hit's geometry planes before evaluating the current one -- two register sets, loop
+                // unrolled by two -- measured slower: 0.477 ms at 66 registers / 7 CTAs, 0.533 ms at 64 / 8 against 0.423 ms)
+                while (hits) {
+                    const int      top  = top_bit(hits);
+                    const uint32_t addr = segbase + top * 16u;
+                    hits ^= bit_at(top);
+                    const float4 ea = lds128(addr);
+                    const float4 eb = lds128(addr + kPlane);
+                    const float4 ec = lds128(addr + 2u * kPlane);
+                    evaluate(ea, eb, ec);
+                }
                 da = Ta < 0.0f;
                 db = Tb < 0.0f;
                 if (__all_sync(FULL, da && db)) break;
@@ -613,8 +627,10 @@ int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32
     const uint2*    rg  = reinterpret_cast<const uint2*>(ranges);
     const uint32_t* ord = (const uint32_t*)ctx->tile_order_ws.ptr;
     const uint32_t* q10 = whole ? d_num_rendered : nullptr;
-    // two pixels per lane, 4 warps per tile; 72 registers -> 7 CTAs per SM (measured: 6 -> 0.489, 7 -> 0.487, 8 (64 registers,
-    // spills) -> 0.630, 10 -> 0.739 ms on the C3 frame)
+    // two pixels per lane, 4 warps per tile, rounds of 128 candidates: 56 registers -> 8 CTAs per SM.  Measured on the C3
+    // frame: one candidate per thread and round at 6 / 7 / 8 / 9 / 10 CTAs per SM 0.451 / 0.432 / 0.420 / 0.439 / 0.463 ms
+    // (10: 48 registers, spills); two candidates per thread (rounds of 256) 5 / 6 / 7 / 8 CTAs 0.524 / 0.487 / 0.486 /
+    // 0.630 ms (8: 64 registers, spills)
     auto kern2 = blend2_kernel<8, 1>;
 #ifdef LCGS_TUNING
     const int occ2 = LCGS_TUNE_INT("LCGS_BLEND2_OCC", 7), cpt = LCGS_TUNE_INT("LCGS_BLEND2_CPT", 2);
