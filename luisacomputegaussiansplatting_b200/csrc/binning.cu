@@ -152,7 +152,9 @@ __device__ __forceinline__ void emit_hist_update(const EmitHist& h, bool emit, u
 // 1080p frame, whose largest Gaussian covers about a thousand tiles.
 constexpr uint32_t kBigPathMinTiles = 12288;
 
-template <bool BIG, bool EXACT_DIV>
+// HIST2: "both digit histograms of the tile sort are accumulated" is a compile-time fact (the fused frame of any picture
+// up to 16 384 tiles): the uniform tests of it leave the expansion loop.
+template <bool BIG, bool EXACT_DIV, bool HIST2 = false>
 __device__ __forceinline__ void duplicate_keys_sorted_body(const uint32_t* __restrict__ d_m, uint32_t m_capacity, uint32_t gx, uint32_t row0,
                                                            const SortedPairsU32& sorted, const uint2* __restrict__ rects,
                                                            unsigned long long* status, uint32_t* ticket,
@@ -167,7 +169,7 @@ __device__ __forceinline__ void duplicate_keys_sorted_body(const uint32_t* __res
     __shared__ uint32_t s_wsum[kEmitWarps];
     __shared__ uint32_t s_base;
     __shared__ uint32_t s_tk;
-    const bool     do_hist = digits.hist != nullptr;
+    const bool     do_hist = HIST2 || digits.hist != nullptr;
     const int      nbins   = do_hist ? (digits.num_passes << digits.radix_bits) : 0;
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -175,7 +177,7 @@ __device__ __forceinline__ void duplicate_keys_sorted_body(const uint32_t* __res
     const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(s_hist);
     const int      sh0 = digits.shift[0] - 32, sh1 = digits.shift[1] - 32;
     const uint32_t m0 = digits.mask[0], m1 = digits.mask[1], hist1_addr = hist_addr + (4u << digits.radix_bits);
-    const bool     two_digits = digits.num_passes > 1;
+    const bool     two_digits = HIST2 || digits.num_passes > 1;
 
     uint32_t M = *d_m;
     if (M > m_capacity) M = m_capacity;
@@ -348,14 +350,14 @@ __device__ __forceinline__ void duplicate_keys_sorted_body(const uint32_t* __res
 
 // Two entry points over one body: the plain kernel takes no big-list parameters at all (with them in its parameter
 // block the compiler re-loaded kernel constants inside the expansion loop: +30 % instructions per step).
-template <bool EXACT_DIV>
+template <bool EXACT_DIV, bool HIST2 = false>
 __global__ void __launch_bounds__(kEmitThreads)
     duplicate_keys_sorted_kernel(const uint32_t* __restrict__ d_m, uint32_t m_capacity, uint32_t gx, uint32_t row0,
                                  const __grid_constant__ SortedPairsU32 sorted, const uint2* __restrict__ rects,
                                  unsigned long long* status, uint32_t* ticket, unsigned long long* __restrict__ keys,
                                  uint32_t* __restrict__ vals, size_t capacity, const __grid_constant__ SortDigits digits)
 {
-    duplicate_keys_sorted_body<false, EXACT_DIV>(d_m, m_capacity, gx, row0, sorted, rects, status, ticket, keys, vals, capacity, digits,
+    duplicate_keys_sorted_body<false, EXACT_DIV, HIST2>(d_m, m_capacity, gx, row0, sorted, rects, status, ticket, keys, vals, capacity, digits,
                                                  BigLists{});
 }
 
@@ -552,6 +554,7 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
         kern<<<blocks, kEmitThreads, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, sorted, rects, status, ticket, k64, vals, capacity, dg, big);
     } else {
         auto kern = exact_div ? duplicate_keys_sorted_kernel<true> : duplicate_keys_sorted_kernel<false>;
+        if (exact_div && dg.hist && dg.num_passes == 2 && LCGS_TUNE_INT("LCGS_EMIT_HIST2", 1)) kern = duplicate_keys_sorted_kernel<true, true>;
         kern<<<blocks, kEmitThreads, 0, s>>>(d_m, (uint32_t)P, gx, (uint32_t)row0, sorted, rects, status, ticket, k64, vals, capacity, dg);
     }
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
