@@ -9,7 +9,9 @@
  * are un-vendored, un-pinned dependencies fetched at configure time: CMakeLists.txt:7-32), so this
  * oracle is a restatement of the reference's DSL kernels, not a build of them.  Only the camera
  * helpers are pinned by the reference's own known-answer tests (test/test_camera.cpp:48-144, see
- * tests/test_oracle_camera.py).  Every other stage is "parity unpinned" by the reference: there is
+ * tests/test_oracle_camera.py); the frame geometry of the output (last tile row / column never rendered,
+ * vertical flip, zero background) is pinned by the reference's published render doc/mip360_bicycle_30000_cuda.png
+ * (tests/test_reference_doc_image.py).  Every other stage is "parity unpinned" by the reference: there is
  * no golden vector, fixture or test for it upstream.  A second, independent numpy restatement
  * (tests/np_restatement.py) cross-checks this file stage by stage.
  *
