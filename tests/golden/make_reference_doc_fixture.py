@@ -9,7 +9,12 @@ what it does pin, independently of the scene, is the frame geometry of the refer
   * neither is the last tile row, and the app flips the image vertically (main.cpp:322-337) -> for H = 1063 = 66*16 + 7
     the TOP 7 rows of the PNG hold the background,
   * the background is black (main.cpp: bg_color 0) and everything next to those bands is rendered.
-Only per-column / per-row maxima of the border region are stored (a few hundred bytes), not the picture.
+  * no pixel of either published render reaches 255 although large areas are saturated (bicycle: 26 328 samples at 252 =
+    floor(255 * 0.99), lego: 1 090 samples at 254 = floor(255 * 0.9999...)): colours are clamped to 1
+    (sh_preprocessor.cpp:152-153), a pixel's accumulated weight stays below 1 (alpha <= 0.99, termination at
+    T < 1e-4, shader.cpp:259-265) and the app TRUNCATES v * 255 (main.cpp:322-337; rounding would give 255).
+Only per-column / per-row maxima of the border region and the top of the value histograms are stored (a few hundred
+bytes), not the pictures.
 
     python tests/golden/make_reference_doc_fixture.py        (needs /root/reference and PIL; run in the build container)
 """
@@ -21,8 +26,11 @@ from PIL import Image
 SRC = "/root/reference/doc/mip360_bicycle_30000_cuda.png"
 im = np.array(Image.open(SRC).convert("RGB"))
 H, W, _ = im.shape
+lego = np.array(Image.open("/root/reference/doc/nerf_blender_lego_30000_cuda.png").convert("RGB"))
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_doc_borders.npz")
 np.savez_compressed(out, W=W, H=H, source=os.path.basename(SRC),
+                    hist_top16_bicycle=np.bincount(im.ravel(), minlength=256)[240:].astype(np.int64),  # values 240..255
+                    hist_top16_lego=np.bincount(lego.ravel(), minlength=256)[240:].astype(np.int64),
                     col_max_right48=im[:, W - 48:].max(axis=(0, 2)).astype(np.uint8),   # per column, last 48 columns
                     row_max_top24=im[:24].max(axis=(1, 2)).astype(np.uint8),            # per row, first 24 rows
                     row_max_bottom24=im[H - 24:].max(axis=(1, 2)).astype(np.uint8),

@@ -8,7 +8,9 @@ scene that covers the whole frame:
   Q1   the last tile column and the last tile row are never rendered (gs_tile_splatter/shader.cpp:102-163),
   flip the app writes the image upside down (app/main.cpp:322-337): the unrendered 7-pixel tile row of a 1063-pixel-high
        frame is at the TOP of the PNG,
-  bg   the untouched pixels are exactly 0 and the bands next to them are rendered.
+  bg   the untouched pixels are exactly 0 and the bands next to them are rendered,
+  255  saturated areas stop at 252 (one alpha-0.99 Gaussian of colour >= 1) and 254, never 255: colour clamp to 1,
+       accumulated weight < 1, truncating uint8(v * 255).
 """
 import os
 
@@ -45,6 +47,29 @@ def test_published_render_shows_q1_and_the_flip():
     assert (W, H) == (1600, 1063)
     # 1600 = 100 tiles exactly: the last tile column is 16 pixels; 1063 = 66 * 16 + 7: the last tile row is 7 pixels high
     assert fixture_geometry() == (16, H - 16 * ((H + 15) // 16 - 1), 0, 0) == (16, 7, 0, 0)
+
+
+def test_published_renders_never_reach_255():
+    for k in ("hist_top16_bicycle", "hist_top16_lego"):
+        assert FIX[k][15] == 0 and FIX[k][:15].sum() > 0
+    assert FIX["hist_top16_bicycle"][12] > 20_000 and FIX["hist_top16_bicycle"][13:].sum() == 0  # saturates at 252
+    assert FIX["hist_top16_lego"][14] > 1_000                                                    # saturates at 254
+
+
+def test_oracle_saturates_like_the_published_renders():
+    # bright, opaque Gaussians stacked in front of the camera: every covered pixel saturates
+    n = 64
+    rng = np.random.default_rng(5)
+    pos = (np.array(scenes.CAM_TARGET, np.float32) + rng.normal(0, 0.05, (n, 3))).astype(np.float32)
+    scale = np.full((n, 3), 0.6, np.float32)
+    rotq = np.tile(np.array([1, 0, 0, 0], np.float32), (n, 1))
+    sh = np.zeros((n, 16, 3), np.float32)
+    sh[:, 0, :] = 10.0  # far above 1 after the +0.5: clamped to 1 by the SH stage
+    cam = orc.make_camera(scenes.CAM_POS, scenes.CAM_TARGET, scenes.world_up("colmap"), 160, 96)
+    one = orc.forward(pos[:1], scale[:1], rotq[:1], sh[:1], np.full(1, 0.999, np.float32), orc.view_params(cam))
+    many = orc.forward(pos, scale, rotq, sh, np.full(n, 0.6, np.float32), orc.view_params(cam))
+    assert orc.image_to_rgb8(one.img).max() == 252   # a single alpha-0.99 Gaussian: floor(255 * 0.99)
+    assert orc.image_to_rgb8(many.img).max() == 254  # accumulated weight 1 - T with T >= 1e-4 -> floor(254.97)
 
 
 def test_oracle_frame_has_the_published_geometry():
