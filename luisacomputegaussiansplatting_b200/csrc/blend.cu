@@ -383,11 +383,7 @@ __device__ __forceinline__ int top_bit(unsigned x)
 }
 
 // CPT = candidates per thread and round (1 or 2): rounds of 128 * CPT list entries, 4 * CPT segments
-// DENSE (CPT = 1): the survivors of the tile cull are packed across the four warps instead of per warp, so a round's
-// consumers walk ceil(survivors / 32) segments, not four.  The packing needs the four warps' counts before anything is
-// stored, and there is still only one barrier per round: the cull + count of round r+2 happens before the barrier of
-// iteration r, the store of round r+1 after it (start of iteration r+1... see the loop), the counts are triple-buffered.
-template <int MIN_CTAS, int CPT, bool DENSE = false>
+template <int MIN_CTAS, int CPT>
 __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
     blend2_kernel(int W, int H, uint32_t gx, uint32_t row0, float bg0, float bg1, float bg2,
                   const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
@@ -399,8 +395,7 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
 
     constexpr int kB2Round = kB2Threads * CPT, kB2Segs = kB2Round / 32;
     __shared__ float4   s_rec[2][3][kB2Round];  // [buffer][plane][slot], planes as in blend_kernel
-    __shared__ __align__(16) uint32_t s_cnt[DENSE ? 3 : 2][kB2Segs];  // per (buffer, segment); DENSE: per (round mod 3, warp)
-    static_assert(!DENSE || CPT == 1, "dense packing is written for one candidate per thread");
+    __shared__ uint32_t s_cnt[2][kB2Segs];
 
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL    = 0xFFFFFFFFu;
@@ -443,47 +438,9 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
         if (lane == 0) s_cnt[buf][seg] = __popc(kept);
     };
 
-    float4   ra0 = make_float4(0.f, 0.f, 0.f, 0.f), rb0 = ra0, rc0 = ra0, ra1, rb1, rc1;
+    float4   ra0, rb0, rc0, ra1, rb1, rc1;
     uint32_t next_id0 = 0, next_id1 = 0;
-    // DENSE: tile cull of the candidate in (ra0, rb0, rc0), this warp's count published for round slot q3 (round mod 3);
-    // returns this lane's rank among the warp's survivors, or 0xFFFFFFFF if it is culled
-    auto cull_count = [&](uint32_t q3, bool valid) -> uint32_t {
-        const bool     keep = valid && !cull_rect_fast(ra0.x, ra0.y, ra0.z, ra0.w, rb0.x, rb0.y, rb0.w, rc0.w, tx0, ty0, tx1, ty1);
-        const unsigned kept = __ballot_sync(FULL, keep);
-        if (lane == 0) s_cnt[q3][warp] = __popc(kept);
-        return keep ? (uint32_t)__popc(kept & lt_mask) : 0xFFFFFFFFu;
-    };
-    // DENSE: store the candidate at its place among ALL survivors of its round (counts of round slot q3 are visible);
-    // entry e of the round sits in segment e >> 5 at slot 31 - (e & 31) (segments are filled from the top): e ^ 31
-    auto store_dense = [&](uint32_t buf, uint32_t q3, uint32_t rank) {
-        const uint4    c    = *reinterpret_cast<const uint4*>(&s_cnt[q3][0]);
-        const uint32_t base = (warp > 0 ? c.x : 0u) + (warp > 1 ? c.y : 0u) + (warp > 2 ? c.z : 0u);
-        if (rank != 0xFFFFFFFFu) {
-            const uint32_t addr = sbase + buf * kBuf + ((base + rank) ^ 31u) * 16u;
-            sts128(addr, ra0);
-            sts128(addr + kPlane, rb0);
-            sts128(addr + 2u * kPlane, rc0);
-        }
-    };
-    uint32_t rank_next = 0xFFFFFFFFu;  // DENSE: rank of the candidate held in registers (round r + 1 at the loop top)
-    if (DENSE) {
-        const bool v0 = (uint32_t)tid < len, v1 = kB2Round + (uint32_t)tid < len;
-        if (v0) {
-            const float4* rec = records + (size_t)__ldg(point_list + range.x + tid) * kRecordFloat4s;
-            ra0 = __ldg(rec); rb0 = __ldg(rec + 1); rc0 = __ldg(rec + 2);
-        }
-        uint32_t id1 = 0;
-        if (v1) id1 = __ldg(point_list + range.x + kB2Round + tid);
-        if (2u * kB2Round + (uint32_t)tid < len) next_id0 = __ldg(point_list + range.x + 2u * kB2Round + tid);  // round 2
-        const uint32_t rank0 = cull_count(0u, v0);
-        __syncthreads();
-        store_dense(0u, 0u, rank0);
-        if (v1) {
-            const float4* rec = records + (size_t)id1 * kRecordFloat4s;
-            ra0 = __ldg(rec); rb0 = __ldg(rec + 1); rc0 = __ldg(rec + 2);
-        }
-        rank_next = cull_count(1u, v1);
-    } else {
+    {
         const bool v0 = (uint32_t)tid < len, v1 = CPT == 2 && (uint32_t)tid + kB2Threads < len;
         if (v0) {
             const float4* rec = records + (size_t)__ldg(point_list + range.x + tid) * kRecordFloat4s;
@@ -504,34 +461,19 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
 
     for (uint32_t r = 0; r < nrounds; r++) {
         const uint32_t buf = r & 1u;
-        uint32_t nidx0, nidx1;
-        bool     nv0, nv1;
-        if (DENSE) {
-            // ---- round r+1 (in registers, counted before the last barrier) goes to the other buffer; then the
-            // gathers of round r+2 are issued (consumed by the cull after the blend below) -------------------------
-            if (r + 1u < nrounds) store_dense(buf ^ 1u, (r + 1u) % 3u, rank_next);
-            nidx0 = (r + 2u) * kB2Round + tid; nidx1 = 0u;
-            nv0 = nidx0 < len; nv1 = false;
-            if (nv0) {
-                const float4* rec = records + (size_t)next_id0 * kRecordFloat4s;
-                ra0 = __ldg(rec); rb0 = __ldg(rec + 1); rc0 = __ldg(rec + 2);
-            }
-            if (nidx0 + kB2Round < len) next_id0 = __ldg(point_list + range.x + nidx0 + kB2Round);
-        } else {
-            // ---- issue the gathers of round r+1 -----------------------------------------------------------------
-            nidx0 = (r + 1u) * kB2Round + tid; nidx1 = nidx0 + kB2Threads;
-            nv0 = nidx0 < len; nv1 = CPT == 2 && nidx1 < len;
-            if (nv0) {
-                const float4* rec = records + (size_t)next_id0 * kRecordFloat4s;
-                ra0 = __ldg(rec); rb0 = __ldg(rec + 1); rc0 = __ldg(rec + 2);
-            }
-            if (nv1) {
-                const float4* rec = records + (size_t)next_id1 * kRecordFloat4s;
-                ra1 = __ldg(rec); rb1 = __ldg(rec + 1); rc1 = __ldg(rec + 2);
-            }
-            if (nidx0 + kB2Round < len) next_id0 = __ldg(point_list + range.x + nidx0 + kB2Round);
-            if (CPT == 2 && nidx1 + kB2Round < len) next_id1 = __ldg(point_list + range.x + nidx1 + kB2Round);
+        // ---- issue the gathers of round r+1 ---------------------------------------------------------------
+        const uint32_t nidx0 = (r + 1u) * kB2Round + tid, nidx1 = nidx0 + kB2Threads;
+        const bool     nv0 = nidx0 < len, nv1 = CPT == 2 && nidx1 < len;
+        if (nv0) {
+            const float4* rec = records + (size_t)next_id0 * kRecordFloat4s;
+            ra0 = __ldg(rec); rb0 = __ldg(rec + 1); rc0 = __ldg(rec + 2);
         }
+        if (nv1) {
+            const float4* rec = records + (size_t)next_id1 * kRecordFloat4s;
+            ra1 = __ldg(rec); rb1 = __ldg(rec + 1); rc1 = __ldg(rec + 2);
+        }
+        if (nidx0 + kB2Round < len) next_id0 = __ldg(point_list + range.x + nidx0 + kB2Round);
+        if (CPT == 2 && nidx1 + kB2Round < len) next_id1 = __ldg(point_list + range.x + nidx1 + kB2Round);
 
         // ---- consume round r -------------------------------------------------------------------------------
         bool da = Ta < 0.0f, db = Tb < 0.0f;
@@ -545,15 +487,9 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
             const float wy0 = (float)(patch_y0 + (int)__reduce_min_sync(FULL, ay));
             const float wx1 = (float)(patch_x0 + (int)__reduce_max_sync(FULL, bx));
             const float wy1 = (float)(patch_y0 + (int)__reduce_max_sync(FULL, by));
-            uint32_t dense_total = 0;
-            if (DENSE) {
-                const uint4 c = *reinterpret_cast<const uint4*>(&s_cnt[r % 3u][0]);
-                dense_total   = c.x + c.y + c.z + c.w;
-            }
-            const int nsegs = DENSE ? (int)((dense_total + 31u) >> 5) : kB2Segs;
 #pragma unroll 1
-            for (int seg = 0; seg < nsegs; seg++) {
-                const uint32_t cnt     = DENSE ? min(32u, dense_total - 32u * (uint32_t)seg) : s_cnt[buf][seg];
+            for (int seg = 0; seg < kB2Segs; seg++) {
+                const uint32_t cnt     = s_cnt[buf][seg];
                 const uint32_t segbase = abase + seg * 512u;
                 bool           hit     = false;
                 if ((uint32_t)lane + cnt >= 32u) {
@@ -594,7 +530,10 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
                     Tb = okb ? (blb ? ttb : -fabsf(Tb)) : Tb;
                 };
                 // (requesting the next hit's geometry planes before evaluating the current one -- two register sets, loop
-                // unrolled by two -- measured slower: 0.477 ms at 66 registers / 7 CTAs, 0.533 ms at 64 / 8 against 0.423 ms)
+                // unrolled by two -- measured slower: 0.477 ms at 66 registers / 7 CTAs, 0.533 ms at 64 / 8 against 0.423 ms;
+                // packing the tile cull's survivors densely across the four warps -- counts triple-buffered, cull + count of
+                // round r+2 before the barrier of round r, store after it -- walks a third fewer segments but measured
+                // 0.430 ms against 0.423: profiles/README.md)
                 while (hits) {
                     const int      top  = top_bit(hits);
                     const uint32_t addr = segbase + top * 16u;
@@ -611,9 +550,7 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
         }
 
         // ---- produce round r+1 into the other buffer --------------------------------------------------------
-        if (DENSE) {
-            rank_next = cull_count((r + 2u) % 3u, nv0);  // round r+2: counted now, stored after the barrier
-        } else if (r + 1u < nrounds) {
+        if (r + 1u < nrounds) {
             produce(buf ^ 1u, 0, nv0, ra0, rb0, rc0);
             if (CPT == 2) produce(buf ^ 1u, 1, nv1, ra1, rb1, rc1);
         }
@@ -711,11 +648,6 @@ int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32
         if (occ2 == 7) kern2 = blend2_kernel<7, 1>;
         if (occ2 == 9) kern2 = blend2_kernel<9, 1>;
         if (occ2 == 10) kern2 = blend2_kernel<10, 1>;
-        if (LCGS_TUNE_INT("LCGS_BLEND2_DENSE", 0)) {
-            kern2 = blend2_kernel<8, 1, true>;
-            if (occ2 == 7) kern2 = blend2_kernel<7, 1, true>;
-            if (occ2 == 9) kern2 = blend2_kernel<9, 1, true>;
-        }
     }
     if (LCGS_TUNE_INT("LCGS_BLEND_P2", 1) == 0) {
         // the one-pixel-per-lane kernel (8x4 patches, 48 registers -> 5 CTAs per SM), kept for A/B runs
