@@ -383,7 +383,7 @@ __device__ __forceinline__ int top_bit(unsigned x)
 }
 
 // CPT = candidates per thread and round (1 or 2): rounds of 128 * CPT list entries, 4 * CPT segments
-template <int MIN_CTAS, int CPT, int VAR = 0>
+template <int MIN_CTAS, int CPT>
 __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
     blend2_kernel(int W, int H, uint32_t gx, uint32_t row0, float bg0, float bg1, float bg2,
                   const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
 
     constexpr int kB2Round = kB2Threads * CPT, kB2Segs = kB2Round / 32;
     __shared__ float4   s_rec[2][3][kB2Round];  // [buffer][plane][slot], planes as in blend_kernel
-    __shared__ __align__(16) uint32_t s_cnt[2][kB2Segs];
+    __shared__ uint32_t s_cnt[2][kB2Segs];
 
     const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL    = 0xFFFFFFFFu;
@@ -487,11 +487,9 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
             const float wy0 = (float)(patch_y0 + (int)__reduce_min_sync(FULL, ay));
             const float wx1 = (float)(patch_x0 + (int)__reduce_max_sync(FULL, bx));
             const float wy1 = (float)(patch_y0 + (int)__reduce_max_sync(FULL, by));
-            uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
-            if ((VAR & 2) && CPT == 1) c4 = *reinterpret_cast<const uint4*>(&s_cnt[buf][0]);
-#pragma unroll (VAR & 1) ? kB2Segs : 1
+#pragma unroll 1
             for (int seg = 0; seg < kB2Segs; seg++) {
-                const uint32_t cnt     = ((VAR & 2) && CPT == 1) ? (seg == 0 ? c4.x : seg == 1 ? c4.y : seg == 2 ? c4.z : c4.w) : s_cnt[buf][seg];
+                const uint32_t cnt     = s_cnt[buf][seg];
                 const uint32_t segbase = abase + seg * 512u;
                 bool           hit     = false;
                 if ((uint32_t)lane + cnt >= 32u) {
@@ -650,10 +648,6 @@ int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32
         if (occ2 == 7) kern2 = blend2_kernel<7, 1>;
         if (occ2 == 9) kern2 = blend2_kernel<9, 1>;
         if (occ2 == 10) kern2 = blend2_kernel<10, 1>;
-        const int var = LCGS_TUNE_INT("LCGS_BLEND2_VAR", 0);
-        if (var == 1) kern2 = blend2_kernel<8, 1, 1>;
-        if (var == 2) kern2 = blend2_kernel<8, 1, 2>;
-        if (var == 3) kern2 = blend2_kernel<8, 1, 3>;
     }
     if (LCGS_TUNE_INT("LCGS_BLEND_P2", 1) == 0) {
         // the one-pixel-per-lane kernel (8x4 patches, 48 registers -> 5 CTAs per SM), kept for A/B runs
