@@ -4,20 +4,22 @@
 // One 128-thread CTA per 16x16 tile; each warp owns an 8x8 pixel patch, each lane two pixels of it
 // (blend2_kernel).  The tile's depth-sorted list is consumed in rounds of 128 candidates through a
 // double-buffered shared-memory stage:
-//   produce (round r+1): every thread gathers one Gaussian's packed 48-byte record (pixel mean,
-//      pre-scaled conic, alpha-test threshold, opacity, colour), tests it against the TILE
-//      rectangle with cull_rect_fast(), and each warp compacts its survivors, order preserved, into its
-//      own 32-slot segment (ballot + popc; no block-wide prefix, no extra barrier);
-//   consume (round r): each warp walks the 4 segments; per segment one lane per survivor tests it
-//      against the bounding box of the warp's unfinished pixels, and only the ballot's set bits are
-//      evaluated, all 64 pixels on the same Gaussian with broadcast LDS.128 and packed FP32 arithmetic.
-// The global gathers of round r+1 are in flight while round r is blended, and there is ONE
-// __syncthreads per round (it also carries the block-wide "every pixel saturated" vote).
+//   produce (round r+1): every thread copies one Gaussian's packed 48-byte record (pixel mean,
+//      pre-scaled conic, alpha-test threshold, log2 opacity, colour, cull quotients) global -> shared
+//      with three 16-byte cp.async (LDGSTS): the record never occupies a register, and the copies land
+//      while round r is blended;
+//   consume (round r): each warp walks the 4 segments of 32 candidates; per segment one lane per
+//      candidate tests it with cull_rect_fast() against the bounding box of the warp's unfinished
+//      pixels, and only the ballot's set bits are evaluated, all 64 pixels on the same Gaussian with
+//      broadcast LDS.128 and packed FP32 arithmetic.
+// There is ONE __syncthreads per round (it also carries the block-wide "every pixel saturated" vote).
 // cull_rect_fast() (lcgs_math.cuh; branch-free, its two divisions precomputed per Gaussian in the
 // record) is conservative with respect to the per-pixel float evaluation, so culling only removes
 // pairs the alpha test would have skipped: on the C3 scene 42 % of the (Gaussian, tile) instances
 // binned by the reference's loose rect never touch their tile -- the reference evaluates all of them
-// for 256 pixels.
+// for 256 pixels.  (MODE 0 / 1 of the kernel, tuning library only: the earlier produce step that
+// gathered through registers and culled against the whole tile first -- it never saved a segment walk,
+// because survivors were compacted per warp.)
 // Other differences that do not change results: colour is staged with the batch instead of fetched
 // from global memory per contributing pair (shader.cpp:268-269); the alpha >= 1/255 test is a
 // compare against a per-Gaussian power threshold, so no exp is needed to reject; the tile stops as
@@ -374,6 +376,12 @@ __device__ __forceinline__ unsigned bit_at(int pos)
     asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(r) : "r"(pos));
     return r;
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS.128): the data never occupies a register
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gptr)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all2() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 // index of the highest set bit (FLO), x != 0
 __device__ __forceinline__ int top_bit(unsigned x)
 {
@@ -383,7 +391,14 @@ __device__ __forceinline__ int top_bit(unsigned x)
 }
 
 // CPT = candidates per thread and round (1 or 2): rounds of 128 * CPT list entries, 4 * CPT segments
-template <int MIN_CTAS, int CPT>
+// MODE 0: the produce step culls each gathered candidate against the whole tile and compacts the survivors per warp.
+// MODE 1: no tile cull -- survivors are compacted per warp, not across warps, so the tile cull never removes a segment
+//         walk, and whatever it removes the patch cull removes too (a candidate it would have dropped costs one lane of
+//         a patch cull that runs anyway).
+// MODE 2 (CPT = 1): as MODE 1, and the records never pass through registers: each thread copies its candidate's three
+//         16-byte planes global -> shared with cp.async (LDGSTS) straight into its slot of the next round's buffer,
+//         waited for before the round's barrier.
+template <int MIN_CTAS, int CPT, int MODE = 0>
 __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
     blend2_kernel(int W, int H, uint32_t gx, uint32_t row0, float bg0, float bg1, float bg2,
                   const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
@@ -425,7 +440,7 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
     // candidate j (0, 1) of a thread is entry j * 128 + tid of the round: warp w's j-th ballot fills segment j * 4 + w,
     // so segment s holds entries [32 s, 32 s + 32) and the consumers meet the list in order
     auto produce = [&](uint32_t buf, int j, bool valid, const float4& a, const float4& b, const float4& c) {
-        const bool     keep = valid && !cull_rect_fast(a.x, a.y, a.z, a.w, b.x, b.y, b.w, c.w, tx0, ty0, tx1, ty1);
+        const bool     keep = valid && (MODE != 0 || !cull_rect_fast(a.x, a.y, a.z, a.w, b.x, b.y, b.w, c.w, tx0, ty0, tx1, ty1));
         const unsigned kept = __ballot_sync(FULL, keep);
         const uint32_t seg  = (uint32_t)(j * kB2Warps + warp);
         if (keep) {
@@ -438,9 +453,28 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
         if (lane == 0) s_cnt[buf][seg] = __popc(kept);
     };
 
+    // MODE 2: entry `lane` of the warp's 32 candidates goes to slot 31 - lane of the warp's segment (filled from the top)
+    auto stage_async = [&](uint32_t buf, bool valid, uint32_t id) {
+        if (valid) {
+            const float4*  rec  = records + (size_t)id * kRecordFloat4s;
+            const uint32_t addr = sbase + buf * kBuf + (uint32_t)(warp * 32 + 31 - lane) * 16u;
+            cp_async_16(addr, rec);  // .ca: with .cg (L1 bypass) the blend measured 0.4215 against 0.412 ms
+            cp_async_16(addr + kPlane, rec + 1);
+            cp_async_16(addr + 2u * kPlane, rec + 2);
+        }
+        const unsigned v = __ballot_sync(FULL, valid);
+        if (lane == 0) s_cnt[buf][warp] = __popc(v);
+    };
+    static_assert(MODE != 2 || CPT == 1, "asynchronous staging is written for one candidate per thread");
+
     float4   ra0, rb0, rc0, ra1, rb1, rc1;
     uint32_t next_id0 = 0, next_id1 = 0;
-    {
+    if (MODE == 2) {
+        const bool v0 = (uint32_t)tid < len;
+        stage_async(0u, v0, v0 ? __ldg(point_list + range.x + tid) : 0u);
+        if (kB2Round + (uint32_t)tid < len) next_id0 = __ldg(point_list + range.x + kB2Round + tid);
+        cp_async_wait_all2();
+    } else {
         const bool v0 = (uint32_t)tid < len, v1 = CPT == 2 && (uint32_t)tid + kB2Threads < len;
         if (v0) {
             const float4* rec = records + (size_t)__ldg(point_list + range.x + tid) * kRecordFloat4s;
@@ -464,7 +498,9 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
         // ---- issue the gathers of round r+1 ---------------------------------------------------------------
         const uint32_t nidx0 = (r + 1u) * kB2Round + tid, nidx1 = nidx0 + kB2Threads;
         const bool     nv0 = nidx0 < len, nv1 = CPT == 2 && nidx1 < len;
-        if (nv0) {
+        if (MODE == 2) {
+            if (r + 1u < nrounds) stage_async(buf ^ 1u, nv0, next_id0);  // lands while round r is blended
+        } else if (nv0) {
             const float4* rec = records + (size_t)next_id0 * kRecordFloat4s;
             ra0 = __ldg(rec); rb0 = __ldg(rec + 1); rc0 = __ldg(rec + 2);
         }
@@ -550,7 +586,9 @@ __global__ void __launch_bounds__(kB2Threads, MIN_CTAS)
         }
 
         // ---- produce round r+1 into the other buffer --------------------------------------------------------
-        if (r + 1u < nrounds) {
+        if (MODE == 2) {
+            cp_async_wait_all2();  // this thread's copies have landed; the barrier publishes everybody's
+        } else if (r + 1u < nrounds) {
             produce(buf ^ 1u, 0, nv0, ra0, rb0, rc0);
             if (CPT == 2) produce(buf ^ 1u, 1, nv1, ra1, rb1, rc1);
         }
@@ -630,24 +668,30 @@ int launch_blend(lcgs_b200_ctx* ctx, int W, int H, const float* bg, const uint32
     const uint2*    rg  = reinterpret_cast<const uint2*>(ranges);
     const uint32_t* ord = (const uint32_t*)ctx->tile_order_ws.ptr;
     const uint32_t* q10 = whole ? d_num_rendered : nullptr;
-    // two pixels per lane, 4 warps per tile, rounds of 128 candidates: 56 registers -> 8 CTAs per SM.  Measured on the C3
-    // frame: one candidate per thread and round at 6 / 7 / 8 / 9 / 10 CTAs per SM 0.451 / 0.432 / 0.420 / 0.439 / 0.463 ms
-    // (10: 48 registers, spills); two candidates per thread (rounds of 256) 5 / 6 / 7 / 8 CTAs 0.524 / 0.487 / 0.486 /
-    // 0.630 ms (8: 64 registers, spills)
-    auto kern2 = blend2_kernel<8, 1>;
+    // two pixels per lane, 4 warps per tile, rounds of 128 candidates staged with cp.async, no cull against the whole tile
+    // (MODE 2): 44 registers at a launch bound of 10 CTAs per SM.  Measured on the C3 frame (blend stage, ms):
+    //   MODE 2 at 8 / 9 / 10 / 11 / 12 CTAs per SM            0.408 / 0.409 / 0.407 / 0.429 / 0.429 (11, 12: spills)
+    //   MODE 1 (registers, no tile cull) at 8                  0.416
+    //   MODE 0 (registers, tile cull + per-warp compaction)    one candidate per thread at 6 / 7 / 8 / 9 / 10 CTAs per SM
+    //                                                          0.451 / 0.432 / 0.420 / 0.439 / 0.463 (10: 48 registers,
+    //                                                          spills); two candidates per thread (rounds of 256) at
+    //                                                          5 / 6 / 7 / 8: 0.524 / 0.487 / 0.486 / 0.630
+    auto kern2 = blend2_kernel<10, 1, 2>;
 #ifdef LCGS_TUNING
-    const int occ2 = LCGS_TUNE_INT("LCGS_BLEND2_OCC", 7), cpt = LCGS_TUNE_INT("LCGS_BLEND2_CPT", 2);
-    if (cpt == 2) {
-        if (occ2 == 4) kern2 = blend2_kernel<4, 2>;
-        if (occ2 == 5) kern2 = blend2_kernel<5, 2>;
-        if (occ2 == 6) kern2 = blend2_kernel<6, 2>;
-        if (occ2 == 8) kern2 = blend2_kernel<8, 2>;
-    } else {
-        kern2 = blend2_kernel<8, 1>;
-        if (occ2 == 6) kern2 = blend2_kernel<6, 1>;
-        if (occ2 == 7) kern2 = blend2_kernel<7, 1>;
-        if (occ2 == 9) kern2 = blend2_kernel<9, 1>;
-        if (occ2 == 10) kern2 = blend2_kernel<10, 1>;
+    {   // A/B selection (tuning library only): LCGS_BLEND2_MODE 0 / 1 / 2, LCGS_BLEND2_CPT 1 / 2 (mode 0), LCGS_BLEND2_OCC
+        const int occ = LCGS_TUNE_INT("LCGS_BLEND2_OCC", 0), cpt = LCGS_TUNE_INT("LCGS_BLEND2_CPT", 1);
+        const int mode = LCGS_TUNE_INT("LCGS_BLEND2_MODE", 2);
+        if (cpt == 2) {
+            kern2 = occ == 5 ? blend2_kernel<5, 2> : occ == 6 ? blend2_kernel<6, 2> : occ == 8 ? blend2_kernel<8, 2> : blend2_kernel<7, 2>;
+        } else if (mode == 0) {
+            kern2 = occ == 6 ? blend2_kernel<6, 1> : occ == 7 ? blend2_kernel<7, 1> : occ == 9 ? blend2_kernel<9, 1>
+                  : occ == 10 ? blend2_kernel<10, 1> : blend2_kernel<8, 1>;
+        } else if (mode == 1) {
+            kern2 = occ == 7 ? blend2_kernel<7, 1, 1> : occ == 9 ? blend2_kernel<9, 1, 1> : blend2_kernel<8, 1, 1>;
+        } else {
+            kern2 = occ == 8 ? blend2_kernel<8, 1, 2> : occ == 9 ? blend2_kernel<9, 1, 2> : occ == 11 ? blend2_kernel<11, 1, 2>
+                  : occ == 12 ? blend2_kernel<12, 1, 2> : blend2_kernel<10, 1, 2>;
+        }
     }
     if (LCGS_TUNE_INT("LCGS_BLEND_P2", 1) == 0) {
         // the one-pixel-per-lane kernel (8x4 patches, 48 registers -> 5 CTAs per SM), kept for A/B runs
