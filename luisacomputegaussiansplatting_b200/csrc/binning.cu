@@ -545,7 +545,7 @@ int launch_duplicate_keys_sorted(lcgs_b200_ctx* ctx, const uint32_t* d_m, int P,
     big.pieces   = (uint2*)((char*)ctx->emit_ws.ptr + entries_bytes);
     big.counters = ticket + 1;
     // persistent CTAs; tiles are handed out by ticket, so CTAs that are not resident yet hold nothing back
-    const uint32_t max_blocks = (uint32_t)ctx->num_sms * 6u;
+    const uint32_t max_blocks = (uint32_t)ctx->num_sms * (uint32_t)LCGS_TUNE_INT("LCGS_EMIT_CTAS", 6);
     const uint32_t blocks     = tiles < max_blocks ? tiles : max_blocks;
     const bool big_path = (unsigned long long)gx * gy >= (unsigned long long)LCGS_TUNE_INT("LCGS_EMIT_BIG_MIN_TILES", (int)kBigPathMinTiles);
     auto* const k64 = reinterpret_cast<unsigned long long*>(keys);

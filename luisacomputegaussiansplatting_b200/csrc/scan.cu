@@ -271,7 +271,7 @@ int launch_scan_compact(lcgs_b200_ctx* ctx, const uint32_t* tiles_touched, const
         LCGS_CUDA_CHECK(ctx, cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s));
     }
     auto* st = (unsigned long long*)ctx->scan_ws.ptr;
-    const uint32_t max_blocks = (uint32_t)ctx->num_sms * 6u;  // persistent: 6 x 256 threads per SM
+    const uint32_t max_blocks = (uint32_t)ctx->num_sms * (uint32_t)LCGS_TUNE_INT("LCGS_SCAN_CTAS", 6);  // persistent: 6 x 256 threads per SM
     scan_compact_kernel<<<tiles < max_blocks ? tiles : max_blocks, kScanThreads, 0, s>>>(tiles_touched, depth, (uint32_t)P, tiles, offsets, ckeys, cvals, st,
                                                        st + tiles, ticket, d_total, d_count, dg, vec_ok);
     LCGS_CUDA_CHECK(ctx, cudaGetLastError());
